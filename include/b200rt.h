@@ -1,0 +1,150 @@
+/*
+ * b200rt.h — C ABI of libb200rt.so, the B200 (sm_100a) path-tracing core.
+ *
+ * This is the drop-in boundary below the reference's renderer plug-in API
+ * (renderers/base_renderer.py:13-16, BaseRenderer.render(scene, camera, settings)).
+ * The reference has no FFI of its own: its device boundary is Numba's JIT
+ * (cuda.to_device / kernel[grid, block](...) / copy_to_host,
+ * renderers/cuda_path_tracer.py:785-805).  Each entry point below names the reference
+ * code it replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; b2rt_last_error() has text;
+ *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensor
+ *     data_ptr()); the library never allocates caller-visible memory; h_* are host pointers
+ *     to small parameter blocks read during the call;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *     asynchronous with respect to the host unless stated otherwise;
+ *   - `precision`: 0 = float32 kernels (production), 1 = float64 kernels compiled with
+ *     -fmad=false (parity instantiation of the SAME templated source); it selects the element
+ *     type "real" of every `real4` array in b2rt_scene;
+ *   - images are in DEVICE ROW ORDER (row 0 = bottom, like the reference kernels,
+ *     cuda_path_tracer.py:27) unless the function says "flipped".
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2RT_PRECISION_F32 0
+#define B2RT_PRECISION_F64 1
+
+/* semantics flags (b2rt_scene.semantics): which reference arithmetic regime the kernels follow */
+#define B2RT_SEM_NUMBA 0 /* cuda_path_tracer.py / cuda_texture_renderer.py: strict t range, `dot > 0` flips   */
+#define B2RT_SEM_CPU   1 /* core/geometry.py via cpu_renderer.py: Plane accepts t == t_max, `dot >= 0` flips */
+
+/* rng modes for b2rt_render_path */
+#define B2RT_RNG_PCG       0 /* counter-based: stream keyed by (pixel, global sample index, seed)        */
+#define B2RT_RNG_REFERENCE 1 /* the reference's int64 xorshift, per-pixel sequential (cuda_path_tracer.py:28,61-71) */
+
+/*
+ * Packed scene in device memory.  Primitive ids ("packed order") are: rectangles [0, n_rect),
+ * spheres [n_rect, n_rect + n_sphere), triangles [.., n_prims) — the scan order of the
+ * reference's cuda_scene_hit (cuda_path_tracer.py:511,582,639); ties resolve to the lowest id.
+ *
+ * real4 record streams (hot = read by intersection, cold = read by shading only):
+ *   d_rect   [4*n_rect]   hot : (anchor.xyz, u_len) (normal.xyz, v_len) (u_unit.xyz, 0) (v_unit.xyz, 0)
+ *   d_sphere [2*n_sphere] hot : (center.xyz, radius) (radius^2, 0, 0, 0)
+ *   d_tri    [3*n_tri]    hot : (v0.xyz, 0) (e1.xyz, 0) (e2.xyz, 0)         e1 = v1 - v0, e2 = v2 - v0
+ *   d_shade  [3*n_prims]  cold: (normal.xyz, 0) (uv0.u, uv0.v, uv1.u, uv1.v) (uv2.u, uv2.v, has_uv, 0)
+ *   d_mat    [2*n_mat]    cold: (color.rgb, diffuse) (specular, reflective, refractive, ior)
+ *   d_lights [n_lights]       : (pos.xyz, 0)
+ * replaces the AoS float32 block of _prepare_scene_data / _prepare_light_data
+ * (cuda_path_tracer.py:819-899,942-946).
+ */
+typedef struct b2rt_scene {
+    int32_t precision;       /* element type of the real4 arrays below */
+    int32_t semantics;       /* B2RT_SEM_* */
+    int32_t n_rect, n_sphere, n_tri;
+    int32_t n_mat, n_tex, n_lights;
+    const void *d_rect, *d_sphere, *d_tri, *d_shade;
+    const int32_t *d_prim_mat;   /* [n_prims] material index                                              */
+    const void *d_mat;
+    const int32_t *d_mat_tex;    /* [n_mat] texture id or -1                                              */
+    const uint32_t *d_texels;    /* RGBX8, one 32-bit load per texel (replaces the flat RGB8 array of
+                                    _prepare_texture_data, cuda_path_tracer.py:901-932)                   */
+    const int32_t *d_tex_info;   /* [4*n_tex]: offset (texels), width, height, 0                          */
+    const void *d_lights;
+    /* LBVH produced by b2rt_lbvh_build (always float32, boxes padded outward) */
+    const void *d_bvh_nodes;     /* float4[4*n_internal]                                                  */
+    const void *d_bvh_top;       /* float4[4*n_top]: breadth-first copy of the top levels (staged in smem)*/
+    int32_t n_bvh_top;
+    int32_t bvh_root;            /* child reference of the root: >= 0 node, < 0 means ~prim               */
+} b2rt_scene;
+
+const char *b2rt_last_error(void);
+int b2rt_version(void);
+/* h_out[0..5] = SM count, max smem per block (opt-in), L2 bytes, SM clock kHz, cc major, cc minor */
+int b2rt_device_info(int device, int64_t *h_out);
+
+/* ---- LBVH (replaces BVHNode.__init__, core/acceleration.py:8-30, with a Morton-code LBVH) -------------- */
+/* bytes of scratch b2rt_lbvh_build needs for n_prims primitives */
+int b2rt_lbvh_temp_bytes(int32_t n_prims, size_t *h_bytes);
+/*
+ * Builds the hierarchy over FLOAT32 geometry streams (same layouts as d_rect/d_sphere/d_tri with
+ * real = float; for an f64 scene pass float copies).  box_pad is added to every box face.
+ * d_nodes_out: float4[4*(n_prims-1)], d_top_out: float4[4*top_capacity].
+ * h_meta_out[0] = n_top, [1] = root reference, [2] = number of internal nodes.
+ * Synchronises the stream before returning (h_meta_out is host memory).
+ */
+int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri,
+                    const void *d_rect_f32, const void *d_sphere_f32, const void *d_tri_f32,
+                    float box_pad, void *d_nodes_out, void *d_top_out, int32_t top_capacity,
+                    int32_t *h_meta_out, void *d_temp, size_t temp_bytes, void *stream);
+
+/* ---- closest hit (replaces cuda_scene_hit, cuda_path_tracer.py:496-730, and Scene.hit, core/scene.py:45) */
+/* One primary ray per pixel at sub-pixel offset (du, dv): u = (x+du)/W, v = (y+dv)/H
+ * (cuda_get_ray, cuda_path_tracer.py:84-112 / Camera.get_ray, core/camera.py:26).
+ * h_cam: 12 doubles origin, lower_left, horizontal, vertical.  d_ids: int32[H*W] packed prim id or -1;
+ * d_t: float64[H*W] hit distance or -1 (may be NULL).  use_bvh = 0 scans all primitives (debug/validation). */
+int b2rt_primary_hits(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
+                      double du, double dv, double t_min, double t_max, int32_t use_bvh,
+                      int32_t *d_ids, double *d_t, void *stream);
+/* Explicit rays: d_o, d_d float64[3*n].  d_rec (optional) float64[9*n]: t, point(3), normal(3), uv(2). */
+int b2rt_trace_rays(const b2rt_scene *scene, int32_t n, const double *d_o, const double *d_d,
+                    double t_min, double t_max, int32_t any_hit, int32_t use_bvh,
+                    int32_t *d_ids, double *d_rec, void *stream);
+
+/* ---- Whitted integrators ------------------------------------------------------------------------------- */
+/* CPURenderer._trace semantics (renderers/cpu_renderer.py:75-151), one sample per pixel.
+ * d_jitter: float64[2*H*W] (du, dv) per pixel or NULL for pixel centres.  h_ambient / h_light_color: 3 doubles.
+ * d_rgb: float64[3*H*W] pre-quantisation colour. */
+int b2rt_render_whitted_cpu(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
+                            const double *d_jitter, int32_t max_depth, const double *h_ambient,
+                            const double *h_light_color, double *d_rgb, void *stream);
+/* cuda_trace_kernel + cuda_trace_ray semantics (renderers/cuda_texture_renderer.py:17-73,173-430):
+ * int(sqrt(spp))^2 jittered samples with the reference's LCG, divided by spp.
+ * d_rgb (optional): float64[3*H*W] mean; d_u8 (optional): uint8[3*H*W] min(255,max(0,int(c*255))). */
+int b2rt_render_whitted_texture(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
+                                int32_t spp, int32_t max_depth, double *d_rgb, uint8_t *d_u8, void *stream);
+
+/* ---- wavefront path tracer (replaces cuda_path_trace_kernel + cuda_trace_path, cuda_path_tracer.py:17-471) */
+/* scratch bytes for a wave of `spp_per_wave` samples per pixel */
+int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, int32_t spp_per_wave,
+                              int32_t max_depth, size_t *h_bytes);
+/*
+ * Adds `spp_local` samples per pixel (global sample indices sample_offset .. sample_offset+spp_local-1)
+ * to d_accum (real[4*H*W]: sum r, g, b, unused), in waves of spp_per_wave.
+ * rng_mode PCG: seed keys the streams.  rng_mode REFERENCE: seed is the reference's frame_count and
+ * d_pixel_rng (int64[H*W], caller-zeroed before sample 0... see DESIGN.md) carries the per-pixel state.
+ * d_counters (optional) uint64[8], accumulated: [0] paths, [1] closest-hit rays, [2] shadow rays,
+ * [3] unshadowed light samples, [4] kernel launches made by this call.
+ */
+int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
+                     int32_t spp_local, int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth,
+                     int32_t rng_mode, uint64_t seed, void *d_accum, int64_t *d_pixel_rng,
+                     void *d_workspace, size_t workspace_bytes, uint64_t *d_counters, void *stream);
+/* mean = accum / spp_total, optional ACES tonemap (cuda_tonemap, :74-81), quantise (:56-58), and write the
+ * FLIPPED image (row 0 = top, replaces np.flip, :807) into d_u8 uint8[3*H*W]. */
+int b2rt_resolve(int32_t precision, const void *d_accum, int32_t width, int32_t height, double spp_total,
+                 int32_t tonemap, uint8_t *d_u8, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H */

@@ -1,0 +1,90 @@
+// rt_math.cuh — scalar/vector helpers templated on the arithmetic type (float = production,
+// double = parity instantiation compiled with -fmad=false).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2rt {
+
+template <typename R> struct Real4;
+template <> struct Real4<float> {
+    using type = float4;
+    static __host__ __device__ __forceinline__ float4 make(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+};
+template <> struct Real4<double> {
+    using type = double4;
+    static __host__ __device__ __forceinline__ double4 make(double a, double b, double c, double d) { return make_double4(a, b, c, d); }
+};
+template <typename R> using real4 = typename Real4<R>::type;
+
+// read-only 4-vector load (LDG.E.128.CONSTANT for float4, two of them for double4)
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ double4 ldg4(const double4 *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+template <typename R> struct V3 {
+    R x, y, z;
+};
+template <typename R> __device__ __forceinline__ V3<R> mk3(R x, R y, R z) { return V3<R>{x, y, z}; }
+template <typename R> __device__ __forceinline__ V3<R> xyz(const real4<R> &v) { return V3<R>{v.x, v.y, v.z}; }
+template <typename R> __device__ __forceinline__ V3<R> operator+(V3<R> a, V3<R> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename R> __device__ __forceinline__ V3<R> operator-(V3<R> a, V3<R> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename R> __device__ __forceinline__ V3<R> operator-(V3<R> a) { return {-a.x, -a.y, -a.z}; }
+template <typename R> __device__ __forceinline__ V3<R> operator*(V3<R> a, R k) { return {a.x * k, a.y * k, a.z * k}; }
+template <typename R> __device__ __forceinline__ V3<R> operator*(R k, V3<R> a) { return {a.x * k, a.y * k, a.z * k}; }
+template <typename R> __device__ __forceinline__ V3<R> operator/(V3<R> a, R k) { return {a.x / k, a.y / k, a.z / k}; }
+template <typename R> __device__ __forceinline__ V3<R> had(V3<R> a, V3<R> b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+// left-to-right dot, the association every reference expression uses (x*x' + y*y' + z*z')
+template <typename R> __device__ __forceinline__ R dot(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ float rsqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+__device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+__device__ __forceinline__ double abs_(double x) { return fabs(x); }
+__device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float pow_(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
+template <typename R> __device__ __forceinline__ R length(V3<R> a) { return sqrt_(a.x * a.x + a.y * a.y + a.z * a.z); }
+// Vec3.normalize (core/math.py:49-53): divide by the length; the zero vector stays zero
+template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) {
+    R l = length(a);
+    return l == R(0) ? V3<R>{R(0), R(0), R(0)} : a / l;
+}
+template <typename R> __device__ __forceinline__ V3<R> cvt3(V3<double> a) { return {R(a.x), R(a.y), R(a.z)}; }
+
+template <typename R> struct Cam {
+    V3<R> origin, llc, hor, ver;
+};
+template <typename R> __host__ inline Cam<R> make_cam(const double *c) {
+    Cam<R> k;
+    k.origin = {R(c[0]), R(c[1]), R(c[2])};
+    k.llc = {R(c[3]), R(c[4]), R(c[5])};
+    k.hor = {R(c[6]), R(c[7]), R(c[8])};
+    k.ver = {R(c[9]), R(c[10]), R(c[11])};
+    return k;
+}
+
+// bit casts between the real type and a same-width integer (queue records carry ints in .w lanes)
+__device__ __forceinline__ float int_as_real(int32_t v, float) { return __int_as_float(v); }
+__device__ __forceinline__ double int_as_real(int64_t v, double) { return __longlong_as_double(v); }
+__device__ __forceinline__ int64_t real_as_int(float v) { return (int64_t)__float_as_int(v); }
+__device__ __forceinline__ int64_t real_as_int(double v) { return __double_as_longlong(v); }
+template <typename R> __device__ __forceinline__ R pack_int(int64_t v) {
+    if constexpr (sizeof(R) == 4) return __int_as_float((int32_t)v);
+    else return __longlong_as_double(v);
+}
+template <typename R> __device__ __forceinline__ uint64_t unpack_u(R v) {
+    if constexpr (sizeof(R) == 4) return (uint64_t)(uint32_t)__float_as_int(v);
+    else return (uint64_t)__double_as_longlong(v);
+}
+
+}  // namespace b2rt
