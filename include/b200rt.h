@@ -144,6 +144,17 @@ int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width
 int b2rt_resolve(int32_t precision, const void *d_accum, int32_t width, int32_t height, double spp_total,
                  int32_t tonemap, uint8_t *d_u8, void *stream);
 
+/* ---- measurement helpers (no reference counterpart: the reference times render() with time.time(),
+ *      main.py:89-91) ----------------------------------------------------------------------------------- */
+/* When on, b2rt_render_path brackets every kernel launch with CUDA events on its stream. */
+int b2rt_profile_enable(int32_t on);
+/* Synchronises the recorded events; h_ms[8] / h_launches[8] = device milliseconds and launch counts since
+ * the last read, per kernel class: 0 raygen, 1 extend, 2 shade, 3 shadow, 4 accumulate. */
+int b2rt_profile_read(double *h_ms, int64_t *h_launches);
+/* FP32 FMA micro-benchmark (8 independent chains per thread, SMs x 8 CTAs x 256 threads): the measured
+ * non-tensor FP32 peak that the FP32 roofline fraction is quoted against. */
+int b2rt_fp32_peak(int32_t iters, double *h_tflops, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,88 @@
+"""ctypes binding of ``libb200rt.so`` (the C ABI of ``include/b200rt.h``).
+
+There is NO CPU fallback: if the library cannot be loaded the import of a renderer fails loudly
+(``RuntimeError``), like the reference's ``_check_cuda_available`` (``cuda_path_tracer.py:741-746``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+P_F32, P_F64 = 0, 1
+RNG_PCG, RNG_REFERENCE = 0, 1
+
+EXPORTS = [
+    "b2rt_last_error", "b2rt_version", "b2rt_device_info", "b2rt_lbvh_temp_bytes", "b2rt_lbvh_build",
+    "b2rt_primary_hits", "b2rt_trace_rays", "b2rt_render_whitted_cpu", "b2rt_render_whitted_texture",
+    "b2rt_path_workspace_bytes", "b2rt_render_path", "b2rt_resolve",
+    "b2rt_profile_enable", "b2rt_profile_read", "b2rt_fp32_peak",
+]
+
+
+class SceneStruct(C.Structure):
+    """``struct b2rt_scene`` (include/b200rt.h)."""
+    _fields_ = [
+        ("precision", C.c_int32), ("semantics", C.c_int32),
+        ("n_rect", C.c_int32), ("n_sphere", C.c_int32), ("n_tri", C.c_int32),
+        ("n_mat", C.c_int32), ("n_tex", C.c_int32), ("n_lights", C.c_int32),
+        ("d_rect", C.c_void_p), ("d_sphere", C.c_void_p), ("d_tri", C.c_void_p), ("d_shade", C.c_void_p),
+        ("d_prim_mat", C.c_void_p), ("d_mat", C.c_void_p), ("d_mat_tex", C.c_void_p),
+        ("d_texels", C.c_void_p), ("d_tex_info", C.c_void_p), ("d_lights", C.c_void_p),
+        ("d_bvh_nodes", C.c_void_p), ("d_bvh_top", C.c_void_p),
+        ("n_bvh_top", C.c_int32), ("bvh_root", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return os.environ.get("B200RT_LIB", _build.LIB_PATH)
+
+
+def load():
+    """Load (building in-tree with nvcc first if the .so is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if "B200RT_LIB" not in os.environ and _build.is_stale():
+        _build.build()
+    if not os.path.isfile(path):
+        raise RuntimeError(f"libb200rt.so not found at {path}; run `python -m b200rt.build` (needs nvcc). "
+                           "b200rt has no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.b2rt_last_error.restype = C.c_char_p
+    vp, i32, i64, u64, dbl, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_size_t
+    SP = C.POINTER(SceneStruct)
+    lib.b2rt_device_info.argtypes = [C.c_int, C.POINTER(i64)]
+    lib.b2rt_lbvh_temp_bytes.argtypes = [i32, C.POINTER(sz)]
+    lib.b2rt_lbvh_build.argtypes = [i32, i32, i32, vp, vp, vp, C.c_float, vp, vp, i32, C.POINTER(i32), vp, sz, vp]
+    lib.b2rt_primary_hits.argtypes = [SP, C.POINTER(dbl), i32, i32, dbl, dbl, dbl, dbl, i32, vp, vp, vp]
+    lib.b2rt_trace_rays.argtypes = [SP, i32, vp, vp, dbl, dbl, i32, i32, vp, vp, vp]
+    lib.b2rt_render_whitted_cpu.argtypes = [SP, C.POINTER(dbl), i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(dbl), vp, vp]
+    lib.b2rt_render_whitted_texture.argtypes = [SP, C.POINTER(dbl), i32, i32, i32, i32, vp, vp, vp]
+    lib.b2rt_path_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, C.POINTER(sz)]
+    lib.b2rt_render_path.argtypes = [SP, C.POINTER(dbl), i32, i32, i32, i64, i32, i32, i32, u64, vp, vp, vp, sz, vp, vp]
+    lib.b2rt_resolve.argtypes = [i32, vp, i32, i32, dbl, i32, vp, vp]
+    lib.b2rt_profile_enable.argtypes = [i32]
+    lib.b2rt_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i64)]
+    lib.b2rt_fp32_peak.argtypes = [i32, C.POINTER(dbl), vp]
+    for name in EXPORTS:
+        if name not in ("b2rt_last_error",):
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().b2rt_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def dbl_array(values):
+    arr = (C.c_double * len(values))(*[float(v) for v in values])
+    return arr

@@ -1,0 +1,314 @@
+"""Scene -> SoA record streams (the layouts of ``include/b200rt.h``).
+
+Replaces the reference's host packers ``_prepare_scene_data`` / ``_prepare_texture_data`` /
+``_prepare_camera_data`` / ``_prepare_light_data`` (``renderers/cuda_path_tracer.py:819-946``,
+identical copies in ``cuda_texture_renderer.py:790-973``).  Differences by design:
+
+* hot (intersection) and cold (shading) attributes go to separate float4 record streams instead of
+  one AoS float block; derived quantities the reference recomputes per ray (rectangle unit axes,
+  triangle edges, radius^2) are computed ONCE here, with the reference's own rounding;
+* textures become RGBX8 (one 32-bit load per texel) and are taken from the already decoded
+  ``Texture.pixels`` — the reference re-opens every JPEG and builds a 52 M-element Python list on
+  every ``render()`` (4.7 s);
+* ``semantics`` selects which of the reference's two arithmetic regimes is reproduced:
+    ``"numba"`` : values rounded to float32 first, float32 arithmetic where Numba types it so
+                  (f32 (+-*/) f32 and ``math.sqrt(f32)`` stay f32: unit axes :552-562, edges :669-675,
+                  ``radius*radius`` :604); planes/triangles are never refractive, only triangles are
+                  textured (:573-574, :630-631, :727-728);
+    ``"cpu"``   : un-rounded float64 objects as ``core/geometry.py`` holds them.
+
+Primitive ids ("packed order") = rectangles, then spheres, then triangles, each in ``scene.objects``
+order — the scan order of ``cuda_scene_hit`` (:511,:582,:639).  ``PackedScene.order`` maps a packed id
+back to ``(index in scene.objects, face index or -1)``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+SEM_NUMBA, SEM_CPU = 0, 1
+_SEM = {"numba": SEM_NUMBA, "cpu": SEM_CPU}
+
+
+class TriangleMesh:
+    """Bulk triangle container (side door for scenes the object-per-triangle API cannot express).
+
+    ``vertices`` float [nv, 3], ``faces`` int [nf, 3], optional per-vertex ``uvs`` float [nv, 2].
+    Drop it into ``scene.objects``; the packer expands it (vectorised) into ``nf`` triangles whose
+    geometric normal is ``normalize((v1-v0) x (v2-v0))`` like ``Triangle.__init__``
+    (``core/geometry.py:130``).
+    """
+
+    def __init__(self, vertices, faces, material, uvs=None):
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(faces, dtype=np.int64).reshape(-1, 3)
+        self.uvs = None if uvs is None else np.ascontiguousarray(uvs, dtype=np.float64).reshape(-1, 2)
+        self.material = material
+
+
+def kind_of(obj) -> str:
+    if isinstance(obj, TriangleMesh):
+        return "mesh"
+    if hasattr(obj, "anchor") and hasattr(obj, "u_dir"):
+        return "plane"
+    if hasattr(obj, "center") and hasattr(obj, "radius"):
+        return "sphere"
+    if hasattr(obj, "v0") and hasattr(obj, "v2"):
+        return "triangle"
+    raise TypeError(f"b200rt cannot pack object of type {type(obj).__name__}")
+
+
+def texture_paths_sorted(scene) -> List[str]:
+    """Distinct ``Texture.path`` strings, sorted: the reference's texture-id rule (:824-832)."""
+    seen: List[str] = []
+    for o in scene.objects:
+        tex = getattr(getattr(o, "material", None), "texture", None)
+        if tex is not None:
+            p = getattr(tex, "path", None)
+            if p and p not in seen:
+                seen.append(p)
+    return sorted(seen)
+
+
+@dataclass
+class PackedScene:
+    semantics: int
+    n_rect: int
+    n_sphere: int
+    n_tri: int
+    rect: np.ndarray          # float64 [4*n_rect, 4]
+    sphere: np.ndarray        # float64 [2*n_sphere, 4]
+    tri: np.ndarray           # float64 [3*n_tri, 4]
+    shade: np.ndarray         # float64 [3*n_prims, 4]
+    prim_mat: np.ndarray      # int32 [n_prims]
+    mat: np.ndarray           # float64 [2*n_mat, 4]
+    mat_tex: np.ndarray       # int32 [n_mat]
+    texels: np.ndarray        # uint32 [total texels]  (R | G<<8 | B<<16 | 0xFF<<24)
+    tex_info: np.ndarray      # int32 [n_tex, 4]: offset, w, h, 0
+    lights: np.ndarray        # float64 [n_lights, 4]
+    order: np.ndarray         # int32 [n_prims, 2]
+    light_color: np.ndarray = field(default_factory=lambda: np.ones(3))
+    ambient: np.ndarray = field(default_factory=lambda: np.full(3, 0.5))
+
+    @property
+    def n_prims(self) -> int:
+        return self.n_rect + self.n_sphere + self.n_tri
+
+    @property
+    def n_mat(self) -> int:
+        return int(self.mat_tex.shape[0])
+
+    @property
+    def n_tex(self) -> int:
+        return int(self.tex_info.shape[0])
+
+    def max_abs_coordinate(self) -> float:
+        m = 0.0
+        if self.n_rect:
+            r = self.rect.reshape(-1, 4, 4)
+            m = max(m, float(np.abs(r[:, 0, :3]).max() + max(r[:, 0, 3].max(), r[:, 1, 3].max())))
+        if self.n_sphere:
+            s = self.sphere.reshape(-1, 2, 4)
+            m = max(m, float((np.abs(s[:, 0, :3]).max(axis=1) + s[:, 0, 3]).max()))
+        if self.n_tri:
+            t = self.tri.reshape(-1, 3, 4)
+            m = max(m, float(np.abs(t[:, 0, :3]).max() + np.abs(t[:, 1:, :3]).max()))
+        return m
+
+
+def _f32(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+def _v(p):
+    return (p.x, p.y, p.z)
+
+
+class _Materials:
+    def __init__(self):
+        self.index: Dict[tuple, int] = {}
+        self.rows: List[tuple] = []
+
+    def get(self, color, diffuse, specular, reflective, refractive, ior, tex) -> int:
+        key = (float(color[0]), float(color[1]), float(color[2]), float(diffuse), float(specular),
+               float(reflective), float(refractive), float(ior), int(tex))
+        if key not in self.index:
+            self.index[key] = len(self.rows)
+            self.rows.append(key)
+        return self.index[key]
+
+
+def pack_camera(camera, semantics: str = "numba") -> np.ndarray:
+    """12 doubles origin, lower_left, horizontal, vertical (``_prepare_camera_data`` :934-940).
+    numba semantics round every component to float32 like the reference's ``np.float32`` array."""
+    c = np.array([*_v(camera.origin), *_v(camera.lower_left_corner), *_v(camera.horizontal), *_v(camera.vertical)],
+                 dtype=np.float64)
+    if _SEM[semantics] == SEM_NUMBA:
+        c = c.astype(np.float32).astype(np.float64)
+    return c
+
+
+def pack_textures(scene):
+    """-> (texels uint32, tex_info int32 [n,4], {path: id}).  Uses the decoded ``Texture.pixels``."""
+    paths = texture_paths_sorted(scene)
+    by_path = {}
+    for o in scene.objects:
+        t = getattr(getattr(o, "material", None), "texture", None)
+        if t is not None and getattr(t, "path", None):
+            by_path.setdefault(t.path, t)
+    chunks, info, off = [], [], 0
+    for p in paths:
+        px = np.ascontiguousarray(by_path[p].pixels, dtype=np.uint8)
+        h, w = px.shape[:2]
+        rgbx = np.empty((h, w, 4), dtype=np.uint8)
+        rgbx[..., :3] = px[..., :3]
+        rgbx[..., 3] = 255
+        chunks.append(rgbx.reshape(-1).view("<u4"))
+        info.append((off, w, h, 0))
+        off += h * w
+    texels = np.concatenate(chunks) if chunks else np.zeros(1, dtype=np.uint32)
+    tex_info = np.array(info, dtype=np.int32).reshape(-1, 4)
+    return texels, tex_info, {p: i for i, p in enumerate(paths)}
+
+
+def pack_scene(scene, semantics: str = "numba", textures=None) -> PackedScene:
+    sem = _SEM[semantics]
+    nb = sem == SEM_NUMBA
+    if textures is None:
+        textures = pack_textures(scene)
+    texels, tex_info, tex_id = textures
+    mats = _Materials()
+
+    def rnd(a):
+        a = np.asarray(a, dtype=np.float64)
+        return a.astype(np.float32).astype(np.float64) if nb else a
+
+    def tex_of(m) -> int:
+        t = getattr(m, "texture", None)
+        if t is None:
+            return -1
+        return tex_id.get(getattr(t, "path", None), -1)
+
+    rects, spheres, tri_hot, tri_cold = [], [], [], []
+    rect_mat, sph_mat, tri_mat = [], [], []
+    rect_nrm = []
+    o_rect, o_sph, o_tri = [], [], []
+
+    for idx, o in enumerate(scene.objects):
+        k, m = kind_of(o), o.material
+        col = rnd(_v(m.color))
+        dif, spe, refl = (float(rnd(x)) for x in (m.diffuse, m.specular, m.reflective))
+        refr = float(rnd(getattr(m, "refractive", 0.0)))
+        ior = float(rnd(getattr(m, "ior", 1.0)))
+        if k == "plane":
+            anchor, normal = rnd(_v(o.anchor)), rnd(_v(o.normal))
+            ul, vl = float(rnd(o.u_len)), float(rnd(o.v_len))
+            if nb:      # in-kernel float32 normalisation of u_dir / v_dir (:552-562)
+                ud, vd = _f32(_v(o.u_dir)), _f32(_v(o.v_dir))
+                un = np.sqrt(ud[0] * ud[0] + ud[1] * ud[1] + ud[2] * ud[2], dtype=np.float32)
+                vn = np.sqrt(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2], dtype=np.float32)
+                if not (un > 0 and vn > 0):
+                    continue                     # the reference can never hit such a plane (:555)
+                uu, vv = (ud / un).astype(np.float64), (vd / vn).astype(np.float64)
+                mid = mats.get(col, dif, spe, refl, 0.0, 1.0, -1)
+            else:       # CPU path: v_unit = normal x u_unit (core/geometry.py:35-36)
+                uu, vv = np.array(_v(o.u_unit)), np.array(_v(o.v_unit))
+                ul, vl = float(o.u_extent), float(o.v_extent)
+                mid = mats.get(col, dif, spe, refl, refr, ior, tex_of(m))
+            rects.append([[*anchor, ul], [*normal, vl], [*uu, 0.0], [*vv, 0.0]])
+            rect_nrm.append(normal)
+            rect_mat.append(mid)
+            o_rect.append((idx, -1))
+        elif k == "sphere":
+            c, r = rnd(_v(o.center)), float(rnd(o.radius))
+            r2 = float(np.float32(r) * np.float32(r)) if nb else r * r
+            spheres.append([[*c, r], [r2, 0.0, 0.0, 0.0]])
+            sph_mat.append(mats.get(col, dif, spe, refl, refr, ior, -1 if nb else tex_of(m)))
+            o_sph.append((idx, -1))
+        elif k == "triangle":
+            v0, v1, v2 = (rnd(_v(p)) for p in (o.v0, o.v1, o.v2))
+            if nb:
+                e1 = (_f32(v1) - _f32(v0)).astype(np.float64)
+                e2 = (_f32(v2) - _f32(v0)).astype(np.float64)
+            else:
+                e1, e2 = v1 - v0, v2 - v0
+            n = rnd(_v(o.normal))
+            if o.uv0 is not None:
+                uv = [float(o.uv0[0]), float(o.uv0[1]), float(o.uv1[0]), float(o.uv1[1]),
+                      float(o.uv2[0]), float(o.uv2[1])]
+                has_uv = 1.0
+            else:           # defaults of the reference packer (:869-874); the CPU path has no uv at all
+                uv, has_uv = [0.0, 0.0, 1.0, 0.0, 1.0, 1.0], (1.0 if nb else 0.0)
+            uv = list(rnd(uv))
+            tri_hot.append([[*v0, 0.0], [*e1, 0.0], [*e2, 0.0]])
+            tri_cold.append([[*n, 0.0], uv[:4], [uv[4], uv[5], has_uv, 0.0]])
+            tri_mat.append(mats.get(col, dif, spe, refl, 0.0 if nb else refr, 1.0 if nb else ior, tex_of(m)))
+            o_tri.append((idx, -1))
+        else:   # mesh
+            V = rnd(o.vertices)
+            F = o.faces
+            v0, v1, v2 = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+            if nb:
+                e1 = (v1.astype(np.float32) - v0.astype(np.float32)).astype(np.float64)
+                e2 = (v2.astype(np.float32) - v0.astype(np.float32)).astype(np.float64)
+            else:
+                e1, e2 = v1 - v0, v2 - v0
+            Vd = np.asarray(o.vertices, dtype=np.float64)
+            nn = np.cross(Vd[F[:, 1]] - Vd[F[:, 0]], Vd[F[:, 2]] - Vd[F[:, 0]])
+            ln = np.linalg.norm(nn, axis=1, keepdims=True)
+            nn = rnd(np.divide(nn, ln, out=np.zeros_like(nn), where=ln > 0))
+            nf = F.shape[0]
+            hot = np.zeros((nf, 3, 4)); hot[:, 0, :3] = v0; hot[:, 1, :3] = e1; hot[:, 2, :3] = e2
+            cold = np.zeros((nf, 3, 4)); cold[:, 0, :3] = nn
+            if o.uvs is not None:
+                U = rnd(o.uvs)
+                cold[:, 1, 0:2] = U[F[:, 0]]; cold[:, 1, 2:4] = U[F[:, 1]]; cold[:, 2, 0:2] = U[F[:, 2]]
+                cold[:, 2, 2] = 1.0
+            else:
+                cold[:, 1, :] = (0.0, 0.0, 1.0, 0.0); cold[:, 2, 0:2] = (1.0, 1.0)
+                cold[:, 2, 2] = 1.0 if nb else 0.0
+            mid = mats.get(col, dif, spe, refl, 0.0 if nb else refr, 1.0 if nb else ior, tex_of(m))
+            tri_hot.append(hot); tri_cold.append(cold)
+            tri_mat.append(np.full(nf, mid, dtype=np.int32))
+            o_tri.append(np.stack([np.full(nf, idx), np.arange(nf)], axis=1))
+
+    def cat(parts, width):
+        arrs = [np.asarray(p, dtype=np.float64).reshape(-1, width, 4) for p in parts]
+        return np.concatenate(arrs).reshape(-1, 4) if arrs else np.zeros((0, 4))
+
+    rect = cat(rects, 4); sphere = cat(spheres, 2); tri = cat(tri_hot, 3)
+    n_rect, n_sphere, n_tri = rect.shape[0] // 4, sphere.shape[0] // 2, tri.shape[0] // 3
+    shade = np.zeros((3 * (n_rect + n_sphere + n_tri), 4))
+    if n_rect:
+        shade.reshape(-1, 3, 4)[:n_rect, 0, :3] = np.asarray(rect_nrm)
+    if n_tri:
+        shade.reshape(-1, 3, 4)[n_rect + n_sphere:] = cat(tri_cold, 3).reshape(-1, 3, 4)
+
+    def cat_i(parts):
+        flat = [np.atleast_1d(np.asarray(p, dtype=np.int32)) for p in parts]
+        return np.concatenate(flat) if flat else np.zeros(0, dtype=np.int32)
+
+    prim_mat = np.concatenate([cat_i(rect_mat), cat_i(sph_mat), cat_i(tri_mat)]).astype(np.int32)
+    order_parts = [np.asarray(p, dtype=np.int32).reshape(-1, 2) for p in (o_rect, o_sph)] + \
+                  [np.asarray(p, dtype=np.int32).reshape(-1, 2) for p in o_tri]
+    order = np.concatenate(order_parts) if order_parts else np.zeros((0, 2), dtype=np.int32)
+
+    mat = np.zeros((2 * max(1, len(mats.rows)), 4))
+    mat_tex = np.full(max(1, len(mats.rows)), -1, dtype=np.int32)
+    for i, row in enumerate(mats.rows):
+        mat[2 * i] = row[0:4]
+        mat[2 * i + 1] = row[4:8]
+        mat_tex[i] = row[8]
+
+    lights = np.zeros((len(scene.lights), 4))
+    for i, l in enumerate(scene.lights):
+        lights[i, :3] = rnd(_v(l))
+
+    lc = getattr(scene, "light_color", None)
+    am = getattr(scene, "ambient", None)
+    return PackedScene(sem, n_rect, n_sphere, n_tri, rect, sphere, tri, shade, prim_mat, mat, mat_tex,
+                       texels, tex_info, lights, order,
+                       np.array(_v(lc)) if lc is not None else np.ones(3),
+                       np.array(_v(am)) if am is not None else np.full(3, 0.5))

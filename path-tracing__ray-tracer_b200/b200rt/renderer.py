@@ -1,0 +1,354 @@
+"""B200 renderers behind the reference's plug-in API (``renderers/base_renderer.py:7-51``).
+
+Three drop-in ``BaseRenderer`` subclasses, one per reference renderer that is on the hot path:
+
+  ``b200_path_tracer``       <- ``cuda_path_raytracer``   (renderers/cuda_path_tracer.py:733-817)
+  ``b200_texture_raytracer`` <- ``cuda_texture_raytracer`` (renderers/cuda_texture_renderer.py:707-788)
+  ``b200_raytracer``         <- ``cpu_raytracer``          (renderers/cpu_renderer.py:14-73)
+
+``render(scene, camera, settings) -> PIL.Image`` keeps the reference contract: RGB8, size
+``(width, height)``, row 0 = top, constructor raises ``RuntimeError`` when no device is usable.
+Python only packs the scene and calls the C ABI; all arithmetic runs in ``libb200rt.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, dist
+from .device import DeviceScene, current_stream_ptr, require_cuda, to_device
+from .packer import pack_camera, pack_scene, pack_textures
+from .plugin import BaseRenderer, RendererFactory
+
+_PREC = {"f32": _lib.P_F32, "f64": _lib.P_F64, 0: _lib.P_F32, 1: _lib.P_F64}
+_RNG = {"pcg": _lib.RNG_PCG, "reference": _lib.RNG_REFERENCE}
+
+
+def _torch_real(precision: int):
+    return torch.float64 if precision == _lib.P_F64 else torch.float32
+
+
+class _TextureCache:
+    """Device copies of RGBX textures keyed by the identity of the decoded ``Texture.pixels`` arrays."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+        self._host = None
+
+    def get(self, scene, device):
+        key = tuple(sorted((getattr(t, "path", ""), id(t.pixels), t.pixels.shape)
+                           for t in {id(o.material.texture): o.material.texture for o in scene.objects
+                                     if getattr(getattr(o, "material", None), "texture", None) is not None}.values()))
+        key = (key, str(device))
+        if key != self._key:
+            texels, tex_info, tex_id = pack_textures(scene)
+            dev = (to_device(texels.view(np.int32), device),
+                   to_device(tex_info if tex_info.shape[0] else np.zeros((1, 4), np.int32), device))
+            self._key, self._val, self._host = key, dev, (texels, tex_info, tex_id)
+            self.uploaded_bytes = int(texels.nbytes)
+        else:
+            self.uploaded_bytes = 0
+        return self._host, self._val
+
+
+class _B200Base(BaseRenderer):
+    semantics = "numba"
+
+    def __init__(self, name: str, precision="f32", device=None, top_nodes: int = 512):
+        super().__init__(name)
+        try:
+            self.device = require_cuda(device)
+            self.lib = _lib.load()
+        except Exception as e:                      # same convention as cuda_path_tracer.py:741-746
+            raise RuntimeError(f"b200rt: CUDA device / library unavailable: {e}")
+        self.precision = _PREC[precision]
+        self.top_nodes = top_nodes
+        self._tex_cache = _TextureCache()
+        self.last_stats: Dict[str, float] = {}
+
+    def _upload(self, scene, camera) -> DeviceScene:
+        host_tex, dev_tex = self._tex_cache.get(scene, self.device)
+        packed = pack_scene(scene, self.semantics, textures=host_tex)
+        cam = pack_camera(camera, self.semantics)
+        reach = float(np.abs(cam[:3]).max())
+        ds = DeviceScene(packed, self.precision, self.device, self.top_nodes, ray_origin_extent=reach,
+                         textures_dev=dev_tex)
+        ds.cam = cam
+        ds.h2d_total = ds.h2d_bytes() - (0 if self._tex_cache.uploaded_bytes else
+                                         ds.texels.numel() * ds.texels.element_size())
+        return ds
+
+    def _image_from_u8(self, u8: torch.Tensor, width: int, height: int):
+        from PIL import Image
+        host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(u8, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return Image.fromarray(host.numpy().reshape(height, width, 3), "RGB")
+
+
+# ------------------------------------------------------------------------------------------ path tracer
+class B200PathTracer(_B200Base):
+    """Wavefront path tracer with the semantics of ``cuda_path_raytracer``.
+
+    kwargs (all optional, forwarded by ``RendererFactory.create(name, **kwargs)``):
+      precision    "f32" (default, production) | "f64" (parity instantiation)
+      rng          "pcg" (default, counter-based) | "reference" (the reference's xorshift, exact replay)
+      seed         RNG seed for "pcg"
+      spp_per_wave samples per pixel processed per wavefront pass (default: fill ~16 M paths)
+    Under ``torch.distributed`` (one process per GPU) the samples are split across ranks and the
+    float accumulation buffers are summed onto rank 0 with one NCCL reduce; only rank 0 returns an image.
+    """
+
+    def __init__(self, precision="f32", rng="pcg", seed: int = 0, spp_per_wave: Optional[int] = None,
+                 device=None, top_nodes: int = 512, wave_paths: int = 1 << 24):
+        super().__init__("b200_path_tracer", precision, device, top_nodes)
+        self.rng_mode = _RNG[rng]
+        self.seed = int(seed)
+        self.spp_per_wave = spp_per_wave
+        self.wave_paths = int(wave_paths)
+        self.frame_count = 0                    # like CUDAPathTracer.frame_count (:739,:809)
+        self._ws = None
+
+    def get_capabilities(self) -> List[str]:
+        return ["path_tracing", "global_illumination", "monte_carlo_integration", "color_bleeding", "shadows",
+                "reflection", "refraction", "textures", "gpu_acceleration", "anti_aliasing", "hdr_rendering",
+                "tone_mapping", "russian_roulette", "importance_sampling", "next_event_estimation",
+                "lbvh_acceleration", "wavefront", "multi_gpu"]
+
+    # -- pieces usable on their own (bench.py times accumulate() with inputs resident in HBM) --------
+    def prepare(self, scene, camera, settings) -> dict:
+        ds = self._upload(scene, camera)
+        W, H, spp, depth = settings.width, settings.height, settings.samples_per_pixel, settings.max_depth
+        rank, world = dist.rank_world()
+        spp_local, offset = dist.split_samples(spp, rank, world)
+        wave = self.spp_per_wave or max(1, min(max(spp_local, 1), self.wave_paths // max(1, W * H)))
+        wave = max(1, min(wave, max(spp_local, 1)))
+        need = C.c_size_t(0)
+        _lib.check(self.lib.b2rt_path_workspace_bytes(self.precision, W, H, wave, depth, C.byref(need)),
+                   "b2rt_path_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value or self._ws.device != self.device:
+            self._ws = None
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        real = _torch_real(self.precision)
+        st = dict(ds=ds, W=W, H=H, spp=spp, depth=depth, spp_local=spp_local, offset=offset, wave=wave,
+                  accum=torch.zeros(W * H * 4, dtype=real, device=self.device),
+                  counters=torch.zeros(8, dtype=torch.int64, device=self.device),
+                  pixel_rng=torch.zeros(W * H, dtype=torch.int64, device=self.device),
+                  u8=torch.empty(W * H * 3, dtype=torch.uint8, device=self.device),
+                  cam=_lib.dbl_array(ds.cam))
+        return st
+
+    def accumulate(self, st: dict) -> None:
+        """Adds this rank's samples to ``st['accum']`` (asynchronous on the current stream)."""
+        seed = self.frame_count if self.rng_mode == _lib.RNG_REFERENCE else self.seed + 0x9E3779B97F4A7C15 * self.frame_count
+        _lib.check(self.lib.b2rt_render_path(
+            st["ds"].ref(), st["cam"], st["W"], st["H"], st["spp_local"], st["offset"], st["wave"], st["depth"],
+            self.rng_mode, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), st["accum"].data_ptr(), st["pixel_rng"].data_ptr(),
+            self._ws.data_ptr(), self._ws.numel(), st["counters"].data_ptr(), current_stream_ptr(self.device)),
+            "b2rt_render_path")
+
+    def resolve(self, st: dict, tonemap: bool = True) -> torch.Tensor:
+        _lib.check(self.lib.b2rt_resolve(self.precision, st["accum"].data_ptr(), st["W"], st["H"],
+                                         float(st["spp"]), 1 if tonemap else 0, st["u8"].data_ptr(),
+                                         current_stream_ptr(self.device)), "b2rt_resolve")
+        return st["u8"]
+
+    def render_accum(self, scene, camera, settings):
+        """float sums [H, W, 4] (device row order) + counters, without tone mapping (tests/analysis)."""
+        with torch.cuda.device(self.device):
+            st = self.prepare(scene, camera, settings)
+            self.accumulate(st)
+            dist.reduce_to_root(st["accum"])
+            torch.cuda.synchronize(self.device)
+            self.frame_count += 1
+            return st["accum"].reshape(st["H"], st["W"], 4).cpu().numpy(), st["counters"].cpu().numpy()
+
+    def render(self, scene, camera, settings):
+        t0 = time.perf_counter()
+        with torch.cuda.device(self.device):
+            st = self.prepare(scene, camera, settings)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            self.accumulate(st)
+            ev1.record()
+            dist.reduce_to_root(st["accum"])
+            rank, world = dist.rank_world()
+            img = None
+            if rank == 0:
+                img = self._image_from_u8(self.resolve(st), st["W"], st["H"])
+            torch.cuda.synchronize(self.device)
+            cnt = st["counters"].cpu().numpy()
+            kernel_s = ev0.elapsed_time(ev1) * 1e-3
+        self.frame_count += 1
+        self.last_stats = dict(paths=int(cnt[0]), closest_rays=int(cnt[1]), shadow_rays=int(cnt[2]),
+                               unshadowed=int(cnt[3]), launches=int(cnt[4]), kernel_s=kernel_s,
+                               wall_s=time.perf_counter() - t0, h2d_bytes=int(st["ds"].h2d_total),
+                               d2h_bytes=st["W"] * st["H"] * 3, spp_local=st["spp_local"], wave=st["wave"],
+                               bvh_nodes=st["ds"].n_internal, bvh_top=st["ds"].n_top)
+        return img
+
+
+# ------------------------------------------------------------------------------------------ textured Whitted
+class B200TextureRaytracer(_B200Base):
+    """Deterministic textured Whitted ray tracer with the semantics of ``cuda_texture_raytracer``."""
+
+    def __init__(self, precision="f32", device=None, top_nodes: int = 512):
+        super().__init__("b200_texture_raytracer", precision, device, top_nodes)
+
+    def get_capabilities(self) -> List[str]:
+        return ["ray_tracing", "shadows", "reflection", "refraction", "textures", "gpu_acceleration",
+                "anti_aliasing", "all_geometry_types", "lbvh_acceleration"]
+
+    def render_float(self, scene, camera, settings):
+        """(mean float64 [H, W, 3], uint8 [H, W, 3]) in device row order (row 0 = bottom)."""
+        with torch.cuda.device(self.device):
+            ds = self._upload(scene, camera)
+            W, H = settings.width, settings.height
+            rgb = torch.empty(W * H * 3, dtype=torch.float64, device=self.device)
+            u8 = torch.empty(W * H * 3, dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.b2rt_render_whitted_texture(ds.ref(), _lib.dbl_array(ds.cam), W, H,
+                                                            settings.samples_per_pixel, settings.max_depth,
+                                                            rgb.data_ptr(), u8.data_ptr(),
+                                                            current_stream_ptr(self.device)),
+                       "b2rt_render_whitted_texture")
+            torch.cuda.synchronize(self.device)
+            return rgb.reshape(H, W, 3).cpu().numpy(), u8.reshape(H, W, 3).cpu().numpy()
+
+    def render(self, scene, camera, settings):
+        t0 = time.perf_counter()
+        with torch.cuda.device(self.device):
+            ds = self._upload(scene, camera)
+            W, H = settings.width, settings.height
+            u8 = torch.empty(W * H * 3, dtype=torch.uint8, device=self.device)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            _lib.check(self.lib.b2rt_render_whitted_texture(ds.ref(), _lib.dbl_array(ds.cam), W, H,
+                                                            settings.samples_per_pixel, settings.max_depth,
+                                                            None, u8.data_ptr(), current_stream_ptr(self.device)),
+                       "b2rt_render_whitted_texture")
+            ev1.record()
+            flipped = torch.flip(u8.reshape(H, W, 3), dims=[0]).contiguous()        # :782 np.flip
+            img = self._image_from_u8(flipped.reshape(-1), W, H)
+            kernel_s = ev0.elapsed_time(ev1) * 1e-3
+        grid_n = int(math.sqrt(settings.samples_per_pixel))
+        self.last_stats = dict(primary=W * H * grid_n * grid_n, kernel_s=kernel_s, wall_s=time.perf_counter() - t0,
+                               h2d_bytes=int(ds.h2d_total), d2h_bytes=W * H * 3)
+        return img
+
+
+# ------------------------------------------------------------------------------------------ CPU-semantics Whitted
+class B200WhittedRenderer(_B200Base):
+    """Whitted ray tracer with the semantics of ``cpu_raytracer`` (both reflection and refraction
+    children traced, BVH closest hit, 16 shadowed light samples).  ``jitter_seed=None`` samples pixel
+    centres; otherwise a seeded jittered grid like ``cpu_renderer.py:40-56``."""
+
+    semantics = "cpu"
+
+    def __init__(self, precision="f64", device=None, top_nodes: int = 512, jitter_seed: Optional[int] = 0):
+        super().__init__("b200_raytracer", precision, device, top_nodes)
+        self.jitter_seed = jitter_seed
+
+    def get_capabilities(self) -> List[str]:
+        return ["ray_tracing", "shadows", "reflection", "refraction", "area_lights", "anti_aliasing",
+                "bvh_acceleration", "textures", "gpu_acceleration"]
+
+    def trace(self, scene, camera, width, height, max_depth, jitter: Optional[np.ndarray] = None) -> np.ndarray:
+        """One sample per pixel -> float64 [H, W, 3] (device row order).  jitter: [H, W, 2] or None."""
+        with torch.cuda.device(self.device):
+            ds = self._upload(scene, camera)
+            rgb = torch.empty(width * height * 3, dtype=torch.float64, device=self.device)
+            jit = to_device(np.ascontiguousarray(jitter, dtype=np.float64), self.device) if jitter is not None else None
+            _lib.check(self.lib.b2rt_render_whitted_cpu(
+                ds.ref(), _lib.dbl_array(ds.cam), width, height, jit.data_ptr() if jit is not None else None,
+                max_depth, _lib.dbl_array(ds.packed.ambient), _lib.dbl_array(ds.packed.light_color),
+                rgb.data_ptr(), current_stream_ptr(self.device)), "b2rt_render_whitted_cpu")
+            torch.cuda.synchronize(self.device)
+            return rgb.reshape(height, width, 3).cpu().numpy()
+
+    def render(self, scene, camera, settings):
+        from PIL import Image
+        t0 = time.perf_counter()
+        W, H = settings.width, settings.height
+        grid_n = max(1, int(math.sqrt(settings.samples_per_pixel)))
+        rng = np.random.default_rng(self.jitter_seed) if self.jitter_seed is not None else None
+        with torch.cuda.device(self.device):
+            ds = self._upload(scene, camera)
+            total = torch.zeros(W * H * 3, dtype=torch.float64, device=self.device)
+            rgb = torch.empty_like(total)
+            for a in range(grid_n):
+                for b in range(grid_n):
+                    if rng is None:
+                        jit = np.full((H, W, 2), 0.5)
+                    else:
+                        jit = rng.random((H, W, 2))
+                    jit[..., 0] = (a + jit[..., 0]) / grid_n
+                    jit[..., 1] = (b + jit[..., 1]) / grid_n
+                    jd = to_device(jit, self.device)
+                    _lib.check(self.lib.b2rt_render_whitted_cpu(
+                        ds.ref(), _lib.dbl_array(ds.cam), W, H, jd.data_ptr(), settings.max_depth,
+                        _lib.dbl_array(ds.packed.ambient), _lib.dbl_array(ds.packed.light_color),
+                        rgb.data_ptr(), current_stream_ptr(self.device)), "b2rt_render_whitted_cpu")
+                    total += rgb
+            total /= settings.samples_per_pixel                                   # :58
+            q = torch.clamp((total * 255).to(torch.int64), 0, 255).to(torch.uint8)   # :59-61
+            img = torch.flip(q.reshape(H, W, 3), dims=[0]).contiguous()            # :62
+            out = self._image_from_u8(img.reshape(-1), W, H)
+        self.last_stats = dict(primary=W * H * grid_n * grid_n, wall_s=time.perf_counter() - t0)
+        return out
+
+
+# ------------------------------------------------------------------------------------------ functional helpers
+def primary_hits(scene, camera, width, height, semantics="numba", precision="f64", du=0.5, dv=0.5,
+                 t_min=None, t_max=None, use_bvh=True, device=None, top_nodes=512):
+    """Primary-ray primitive ids -> (ids [H, W] int32 index into scene.objects or -1, t [H, W], packed ids)."""
+    lib = _lib.load()
+    device = require_cuda(device)
+    with torch.cuda.device(device):
+        packed = pack_scene(scene, semantics)
+        cam = pack_camera(camera, semantics)
+        ds = DeviceScene(packed, _PREC[precision], device, top_nodes, ray_origin_extent=float(np.abs(cam[:3]).max()))
+        ids = torch.empty(width * height, dtype=torch.int32, device=device)
+        tt = torch.empty(width * height, dtype=torch.float64, device=device)
+        if t_min is None:
+            t_min = 1e-3 if semantics == "cpu" else 0.001
+        if t_max is None:
+            t_max = float("inf") if semantics == "cpu" else 1000000.0
+        _lib.check(lib.b2rt_primary_hits(ds.ref(), _lib.dbl_array(cam), width, height, du, dv, t_min, t_max,
+                                         1 if use_bvh else 0, ids.data_ptr(), tt.data_ptr(),
+                                         current_stream_ptr(device)), "b2rt_primary_hits")
+        torch.cuda.synchronize(device)
+        pid = ids.cpu().numpy().reshape(height, width)
+        obj = np.where(pid >= 0, packed.order[np.maximum(pid, 0), 0], -1).astype(np.int32)
+        return obj, tt.cpu().numpy().reshape(height, width), pid
+
+
+def trace_rays(scene, origins, dirs, semantics="numba", precision="f64", t_min=0.001, t_max=1000000.0,
+               any_hit=False, use_bvh=True, device=None, top_nodes=512, packed=None):
+    """Closest/any hit for explicit rays -> (packed ids [n], rec [n, 9]: t, point, normal, uv)."""
+    lib = _lib.load()
+    device = require_cuda(device)
+    with torch.cuda.device(device):
+        packed = packed or pack_scene(scene, semantics)
+        ds = DeviceScene(packed, _PREC[precision], device, top_nodes,
+                         ray_origin_extent=float(np.abs(np.asarray(origins)).max()))
+        o = to_device(np.ascontiguousarray(origins, dtype=np.float64), device)
+        d = to_device(np.ascontiguousarray(dirs, dtype=np.float64), device)
+        n = int(o.numel() // 3)
+        ids = torch.empty(n, dtype=torch.int32, device=device)
+        rec = torch.empty(n * 9, dtype=torch.float64, device=device)
+        _lib.check(lib.b2rt_trace_rays(ds.ref(), n, o.data_ptr(), d.data_ptr(), t_min, t_max, 1 if any_hit else 0,
+                                       1 if use_bvh else 0, ids.data_ptr(), rec.data_ptr(),
+                                       current_stream_ptr(device)), "b2rt_trace_rays")
+        torch.cuda.synchronize(device)
+        return ids.cpu().numpy(), rec.cpu().numpy().reshape(n, 9)
+
+
+RendererFactory.register("b200_path_tracer", B200PathTracer)
+RendererFactory.register("b200_texture_raytracer", B200TextureRaytracer)
+RendererFactory.register("b200_raytracer", B200WhittedRenderer)

@@ -1,0 +1,230 @@
+// c_api.cu — the extern "C" surface declared in include/b200rt.h.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/b200rt.h"
+#include "lbvh.h"
+#include "rt_api.h"
+
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(const char *where, cudaError_t e) {
+    snprintf(g_err, sizeof g_err, "%s: %s", where, cudaGetErrorString(e));
+    return 1;
+}
+int fail_msg(const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return 2;
+}
+inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define DISPATCH(scene_precision, call_f32, call_f64)                                   \
+    ((scene_precision) == B2RT_PRECISION_F64 ? (call_f64) : (call_f32))
+}  // namespace
+
+using b2rt::Api;
+
+// ---- per-kernel-class event timing ----------------------------------------------------------------
+namespace b2rt {
+namespace {
+struct ProfRec { int cls; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+void prof_begin(int cls, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r{cls, prof_event(), prof_event()};
+    cudaEventRecord(r.a, st);
+    g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof_recs.empty()) return;
+    cudaEventRecord(g_prof_recs.back().b, st);
+}
+}  // namespace b2rt
+
+static __global__ void fp32_peak_kernel(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678f) out[0] = s;
+}
+
+extern "C" {
+
+const char *b2rt_last_error(void) { return g_err; }
+int b2rt_version(void) { return 100; }
+
+int b2rt_device_info(int device, int64_t *h_out) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e) return fail("b2rt_device_info", e);
+    int clock_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, device);
+    h_out[0] = p.multiProcessorCount;
+    h_out[1] = (int64_t)p.sharedMemPerBlockOptin;
+    h_out[2] = p.l2CacheSize;
+    h_out[3] = clock_khz;
+    h_out[4] = p.major;
+    h_out[5] = p.minor;
+    return 0;
+}
+
+int b2rt_lbvh_temp_bytes(int32_t n_prims, size_t *h_bytes) {
+    *h_bytes = b2rt::lbvh_temp_bytes(n_prims);
+    return 0;
+}
+
+int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri, const void *d_rect, const void *d_sphere,
+                    const void *d_tri, float box_pad, void *d_nodes_out, void *d_top_out, int32_t top_capacity,
+                    int32_t *h_meta_out, void *d_temp, size_t temp_bytes, void *stream) {
+    if (top_capacity > b2rt::kTopMax) top_capacity = b2rt::kTopMax;
+    if (top_capacity < 0) top_capacity = 0;
+    int meta[3];
+    cudaError_t e = b2rt::lbvh_build(n_rect, n_sphere, n_tri, (const float4 *)d_rect, (const float4 *)d_sphere,
+                                     (const float4 *)d_tri, box_pad, (float4 *)d_nodes_out, (float4 *)d_top_out,
+                                     top_capacity, meta, d_temp, temp_bytes, S(stream));
+    if (e) return fail("b2rt_lbvh_build", e);
+    h_meta_out[0] = meta[0]; h_meta_out[1] = meta[1]; h_meta_out[2] = meta[2];
+    return 0;
+}
+
+static int check_scene(const b2rt_scene *s) {
+    if (!s) return fail_msg("scene is NULL");
+    if (s->precision != B2RT_PRECISION_F32 && s->precision != B2RT_PRECISION_F64) return fail_msg("bad precision");
+    if (s->n_bvh_top < 0 || s->n_bvh_top > b2rt::kTopMax) return fail_msg("n_bvh_top out of range");
+    return 0;
+}
+
+int b2rt_primary_hits(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height, double du,
+                      double dv, double t_min, double t_max, int32_t use_bvh, int32_t *d_ids, double *d_t,
+                      void *stream) {
+    if (int r = check_scene(scene)) return r;
+    cudaError_t e = DISPATCH(scene->precision,
+        Api<float>::primary_hits(scene, h_cam, width, height, du, dv, t_min, t_max, use_bvh, d_ids, d_t, S(stream)),
+        Api<double>::primary_hits(scene, h_cam, width, height, du, dv, t_min, t_max, use_bvh, d_ids, d_t, S(stream)));
+    return e ? fail("b2rt_primary_hits", e) : 0;
+}
+
+int b2rt_trace_rays(const b2rt_scene *scene, int32_t n, const double *d_o, const double *d_d, double t_min,
+                    double t_max, int32_t any_hit, int32_t use_bvh, int32_t *d_ids, double *d_rec, void *stream) {
+    if (int r = check_scene(scene)) return r;
+    cudaError_t e = DISPATCH(scene->precision,
+        Api<float>::trace_rays(scene, n, d_o, d_d, t_min, t_max, any_hit, use_bvh, d_ids, d_rec, S(stream)),
+        Api<double>::trace_rays(scene, n, d_o, d_d, t_min, t_max, any_hit, use_bvh, d_ids, d_rec, S(stream)));
+    return e ? fail("b2rt_trace_rays", e) : 0;
+}
+
+int b2rt_render_whitted_cpu(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
+                            const double *d_jitter, int32_t max_depth, const double *h_ambient,
+                            const double *h_light_color, double *d_rgb, void *stream) {
+    if (int r = check_scene(scene)) return r;
+    if (max_depth < 0 || max_depth > 20) return fail_msg("whitted_cpu: max_depth must be in [0, 20]");
+    cudaError_t e = DISPATCH(scene->precision,
+        Api<float>::whitted_cpu(scene, h_cam, width, height, d_jitter, max_depth, h_ambient, h_light_color, d_rgb, S(stream)),
+        Api<double>::whitted_cpu(scene, h_cam, width, height, d_jitter, max_depth, h_ambient, h_light_color, d_rgb, S(stream)));
+    return e ? fail("b2rt_render_whitted_cpu", e) : 0;
+}
+
+int b2rt_render_whitted_texture(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
+                                int32_t spp, int32_t max_depth, double *d_rgb, uint8_t *d_u8, void *stream) {
+    if (int r = check_scene(scene)) return r;
+    if (spp < 1) return fail_msg("whitted_texture: spp must be >= 1");
+    cudaError_t e = DISPATCH(scene->precision,
+        Api<float>::whitted_texture(scene, h_cam, width, height, spp, max_depth, d_rgb, d_u8, S(stream)),
+        Api<double>::whitted_texture(scene, h_cam, width, height, spp, max_depth, d_rgb, d_u8, S(stream)));
+    return e ? fail("b2rt_render_whitted_texture", e) : 0;
+}
+
+int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, int32_t spp_per_wave,
+                              int32_t max_depth, size_t *h_bytes) {
+    if (width < 1 || height < 1 || spp_per_wave < 1 || max_depth < 1) return fail_msg("path_workspace_bytes: bad size");
+    *h_bytes = precision == B2RT_PRECISION_F64 ? Api<double>::path_workspace_bytes(width, height, spp_per_wave, max_depth)
+                                               : Api<float>::path_workspace_bytes(width, height, spp_per_wave, max_depth);
+    return 0;
+}
+
+int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height, int32_t spp_local,
+                     int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth, int32_t rng_mode, uint64_t seed,
+                     void *d_accum, int64_t *d_pixel_rng, void *d_workspace, size_t workspace_bytes,
+                     uint64_t *d_counters, void *stream) {
+    if (int r = check_scene(scene)) return r;
+    if (max_depth < 1) return fail_msg("render_path: max_depth must be >= 1");
+    if ((long long)width * height * (long long)(spp_per_wave < 1 ? 1 : spp_per_wave) > 0x7fffffffLL)
+        return fail_msg("render_path: wave larger than 2^31 paths");
+    b2rt::PathArgs a;
+    a.width = width; a.height = height; a.spp_local = spp_local; a.spp_per_wave = spp_per_wave;
+    a.max_depth = max_depth; a.rng_mode = rng_mode; a.sample_offset = sample_offset; a.seed = seed;
+    a.accum = d_accum; a.pixel_rng = (long long *)d_pixel_rng; a.workspace = d_workspace;
+    a.workspace_bytes = workspace_bytes; a.counters = (unsigned long long *)d_counters;
+    cudaError_t e = DISPATCH(scene->precision, Api<float>::render_path(scene, h_cam, a, S(stream)),
+                             Api<double>::render_path(scene, h_cam, a, S(stream)));
+    return e ? fail("b2rt_render_path", e) : 0;
+}
+
+int b2rt_resolve(int32_t precision, const void *d_accum, int32_t width, int32_t height, double spp_total,
+                 int32_t tonemap, uint8_t *d_u8, void *stream) {
+    cudaError_t e = DISPATCH(precision, Api<float>::resolve(d_accum, width, height, spp_total, tonemap, d_u8, S(stream)),
+                             Api<double>::resolve(d_accum, width, height, spp_total, tonemap, d_u8, S(stream)));
+    return e ? fail("b2rt_resolve", e) : 0;
+}
+
+int b2rt_profile_enable(int32_t on) {
+    b2rt::g_prof_on = on != 0;
+    return 0;
+}
+
+int b2rt_profile_read(double *h_ms, int64_t *h_launches) {
+    for (int k = 0; k < b2rt::kNumClasses; ++k) { h_ms[k] = 0.0; h_launches[k] = 0; }
+    for (auto &r : b2rt::g_prof_recs) {
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e) return fail("b2rt_profile_read", e);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        h_ms[r.cls] += ms;
+        h_launches[r.cls] += 1;
+        b2rt::g_prof_pool.push_back(r.a);
+        b2rt::g_prof_pool.push_back(r.b);
+    }
+    b2rt::g_prof_recs.clear();
+    return 0;
+}
+
+int b2rt_fp32_peak(int32_t iters, double *h_tflops, void *stream) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    float *out = nullptr;
+    cudaError_t e = cudaMalloc(&out, 16);
+    if (e) return fail("b2rt_fp32_peak", e);
+    const int T = 256, G = sms * 8;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    fp32_peak_kernel<<<G, T, 0, S(stream)>>>(out, 1000, 1.0000001f, 1e-7f);       // warm-up
+    cudaEventRecord(a, S(stream));
+    fp32_peak_kernel<<<G, T, 0, S(stream)>>>(out, iters, 1.0000001f, 1e-7f);
+    cudaEventRecord(b, S(stream));
+    e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    if (e) return fail("b2rt_fp32_peak", e);
+    *h_tflops = (double)G * T * 8.0 * 2.0 * iters / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
+}  // extern "C"

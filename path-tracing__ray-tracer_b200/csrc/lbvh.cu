@@ -1,0 +1,322 @@
+// lbvh.cu — GPU LBVH build: primitive bounds -> 30-bit Morton codes -> radix sort -> Karras (2012)
+// hierarchy -> bottom-up refit with atomic arrival flags -> breadth-first copy of the top levels.
+//
+// Replaces the reference's recursive random-axis median split (BVHNode.__init__,
+// core/acceleration.py:8-30; per-primitive boxes core/geometry.py:40-48,83,131-137;
+// AABB.surrounding_box core/math.py:90-102).  Closest-hit results do not depend on the hierarchy
+// (rt_scene.cuh applies a fixed tie rule), so parity is preserved while the build becomes O(n) sorts
+// and scans.  Leaves hold exactly one primitive (like the reference's leaves).
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lbvh.h"
+
+namespace b2rt {
+
+namespace {
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct Box {
+    float3 lo, hi;
+};
+
+__device__ __forceinline__ void grow(Box &b, float x, float y, float z) {
+    b.lo.x = fminf(b.lo.x, x); b.lo.y = fminf(b.lo.y, y); b.lo.z = fminf(b.lo.z, z);
+    b.hi.x = fmaxf(b.hi.x, x); b.hi.y = fmaxf(b.hi.y, y); b.hi.z = fmaxf(b.hi.z, z);
+}
+
+// boxes of packed primitive i from the float32 hot streams (layouts in include/b200rt.h)
+__device__ Box prim_box(int i, int n_rect, int n_sphere, const float4 *rect, const float4 *sphere, const float4 *tri,
+                        float pad) {
+    Box b;
+    b.lo = make_float3(3.0e38f, 3.0e38f, 3.0e38f);
+    b.hi = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
+    if (i < n_rect) {
+        float4 r0 = rect[4 * i], r1 = rect[4 * i + 1], r2 = rect[4 * i + 2], r3 = rect[4 * i + 3];
+        float ux = r2.x * r0.w, uy = r2.y * r0.w, uz = r2.z * r0.w;
+        float vx = r3.x * r1.w, vy = r3.y * r1.w, vz = r3.z * r1.w;
+        grow(b, r0.x, r0.y, r0.z);
+        grow(b, r0.x + ux, r0.y + uy, r0.z + uz);
+        grow(b, r0.x + vx, r0.y + vy, r0.z + vz);
+        grow(b, r0.x + ux + vx, r0.y + uy + vy, r0.z + uz + vz);
+    } else if (i < n_rect + n_sphere) {
+        float4 s = sphere[2 * (i - n_rect)];
+        grow(b, s.x - s.w, s.y - s.w, s.z - s.w);
+        grow(b, s.x + s.w, s.y + s.w, s.z + s.w);
+    } else {
+        int k = i - n_rect - n_sphere;
+        float4 v0 = tri[3 * k], e1 = tri[3 * k + 1], e2 = tri[3 * k + 2];
+        grow(b, v0.x, v0.y, v0.z);
+        grow(b, v0.x + e1.x, v0.y + e1.y, v0.z + e1.z);
+        grow(b, v0.x + e2.x, v0.y + e2.y, v0.z + e2.z);
+    }
+    // outward pad: absolute pad plus a relative term for large coordinates
+    float ax = fmaxf(fabsf(b.lo.x), fabsf(b.hi.x)), ay = fmaxf(fabsf(b.lo.y), fabsf(b.hi.y)),
+          az = fmaxf(fabsf(b.lo.z), fabsf(b.hi.z));
+    float px = pad + 4e-7f * ax, py = pad + 4e-7f * ay, pz = pad + 4e-7f * az;
+    b.lo.x -= px; b.lo.y -= py; b.lo.z -= pz;
+    b.hi.x += px; b.hi.y += py; b.hi.z += pz;
+    return b;
+}
+
+__global__ void bounds_kernel(int n, int n_rect, int n_sphere, const float4 *rect, const float4 *sphere,
+                              const float4 *tri, float pad, float4 *box_lo, float4 *box_hi, int *scene_bounds) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float c[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};   // centroid bounds
+    if (i < n) {
+        Box b = prim_box(i, n_rect, n_sphere, rect, sphere, tri, pad);
+        box_lo[i] = make_float4(b.lo.x, b.lo.y, b.lo.z, 0.f);
+        box_hi[i] = make_float4(b.hi.x, b.hi.y, b.hi.z, 0.f);
+        c[0] = c[3] = 0.5f * (b.lo.x + b.hi.x);
+        c[1] = c[4] = 0.5f * (b.lo.y + b.hi.y);
+        c[2] = c[5] = 0.5f * (b.lo.z + b.hi.z);
+    }
+    typedef cub::BlockReduce<float, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    for (int k = 0; k < 6; ++k) {
+        float r = k < 3 ? BR(tmp).Reduce(c[k], cub::Min()) : BR(tmp).Reduce(c[k], cub::Max());
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (k < 3) atomicMin(scene_bounds + k, float_to_ordered(r));
+            else atomicMax(scene_bounds + k, float_to_ordered(r));
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void morton_kernel(int n, const float4 *box_lo, const float4 *box_hi, const int *scene_bounds,
+                              uint32_t *keys, int *vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lo[3], ext[3];
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = ordered_to_float(scene_bounds[k]);
+        ext[k] = fmaxf(ordered_to_float(scene_bounds[3 + k]) - lo[k], 1e-20f);
+    }
+    float4 a = box_lo[i], b = box_hi[i];
+    float cx = (0.5f * (a.x + b.x) - lo[0]) / ext[0];
+    float cy = (0.5f * (a.y + b.y) - lo[1]) / ext[1];
+    float cz = (0.5f * (a.z + b.z) - lo[2]) / ext[2];
+    uint32_t qx = (uint32_t)fminf(fmaxf(cx * 1024.f, 0.f), 1023.f);
+    uint32_t qy = (uint32_t)fminf(fmaxf(cy * 1024.f, 0.f), 1023.f);
+    uint32_t qz = (uint32_t)fminf(fmaxf(cz * 1024.f, 0.f), 1023.f);
+    keys[i] = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
+    vals[i] = i;
+}
+
+// common-prefix length of sorted keys i and j (Karras 2012, with the index as tie-break bits)
+__device__ __forceinline__ int delta(const uint32_t *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+
+__global__ void hierarchy_kernel(int n, const uint32_t *keys, const int *vals, int2 *children, int *parent_node,
+                                 int *parent_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int2 c;
+    if (lo == gamma) { c.x = ~vals[gamma]; parent_leaf[gamma] = i; } else { c.x = gamma; parent_node[gamma] = i; }
+    if (hi == gamma + 1) { c.y = ~vals[gamma + 1]; parent_leaf[gamma + 1] = i; } else { c.y = gamma + 1; parent_node[gamma + 1] = i; }
+    children[i] = c;
+    if (i == 0) parent_node[0] = -1;
+}
+
+// Bottom-up refit.  One thread per leaf climbs; the second arrival at a node (atomic flag) owns it.
+__global__ void refit_kernel(int n, const int2 *children, const int *parent_node, const int *parent_leaf,
+                             const float4 *box_lo, const float4 *box_hi, int *flags, float4 *node_lo, float4 *node_hi,
+                             float4 *nodes) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int cur = parent_leaf[k];
+    while (cur >= 0) {
+        __threadfence();
+        if (atomicAdd(flags + cur, 1) == 0) return;
+        int2 c = children[cur];
+        float4 llo, lhi, rlo, rhi;
+        if (c.x < 0) { llo = box_lo[~c.x]; lhi = box_hi[~c.x]; }
+        else { llo = __ldcg(node_lo + c.x); lhi = __ldcg(node_hi + c.x); }
+        if (c.y < 0) { rlo = box_lo[~c.y]; rhi = box_hi[~c.y]; }
+        else { rlo = __ldcg(node_lo + c.y); rhi = __ldcg(node_hi + c.y); }
+        nodes[4 * (size_t)cur + 0] = make_float4(llo.x, llo.y, llo.z, lhi.x);
+        nodes[4 * (size_t)cur + 1] = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
+        nodes[4 * (size_t)cur + 2] = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
+        nodes[4 * (size_t)cur + 3] = make_float4(__int_as_float(c.x), __int_as_float(c.y), 0.f, 0.f);
+        node_lo[cur] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
+        node_hi[cur] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+        cur = parent_node[cur];
+    }
+}
+
+// Level-synchronous breadth-first numbering of the first `cap` internal nodes (one CTA).
+// top_id[node] = position in the smem-staged copy, or -1.
+__global__ void __launch_bounds__(1024)
+top_order_kernel(int n_internal, const int2 *children, int cap, int *top_id, int *order, int *meta) {
+    typedef cub::BlockScan<int, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int s_begin, s_end;
+    if (threadIdx.x == 0) {
+        s_begin = 0; s_end = 0;
+        if (n_internal > 0 && cap > 0) { order[0] = 0; top_id[0] = 0; s_end = 1; }
+    }
+    __syncthreads();
+    while (true) {
+        int begin = s_begin, end = s_end;
+        if (begin >= end || end >= cap) break;
+        // a level can be wider than the CTA: walk it in chunks, appending in order
+        for (int base = begin; base < end; base += blockDim.x) {
+            int t = base + threadIdx.x;
+            int c0 = -1, c1 = -1;
+            if (t < end) {
+                int2 c = children[order[t]];
+                if (c.x >= 0) c0 = c.x;
+                if (c.y >= 0) c1 = c.y;
+            }
+            int cnt = (c0 >= 0) + (c1 >= 0), pos, total;
+            Scan(tmp).ExclusiveSum(cnt, pos, total);
+            int tail = s_end;
+            __syncthreads();
+            if (c0 >= 0) { int p = tail + pos; if (p < cap) { order[p] = c0; top_id[c0] = p; } ++pos; }
+            if (c1 >= 0) { int p = tail + pos; if (p < cap) { order[p] = c1; top_id[c1] = p; } }
+            if (threadIdx.x == 0) s_end = min(cap, tail + total);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) s_begin = end;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        meta[0] = s_end;                                   // n_top
+        meta[2] = n_internal;
+    }
+}
+
+// Rewrites child references into the final encoding (node in top: its top index; other node:
+// n_top + index; leaf: ~prim) and emits the breadth-first top copy.
+__global__ void finalize_kernel(int n_internal, const int *top_id, int *meta, float4 *nodes, float4 *top) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_top = meta[0];
+    if (i == 0) meta[1] = n_internal > 0 ? (top_id[0] >= 0 ? top_id[0] : n_top) : -1;
+    if (i >= n_internal) return;
+    float4 n3 = nodes[4 * (size_t)i + 3];
+    int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+    if (cl >= 0) cl = top_id[cl] >= 0 ? top_id[cl] : n_top + cl;
+    if (cr >= 0) cr = top_id[cr] >= 0 ? top_id[cr] : n_top + cr;
+    n3 = make_float4(__int_as_float(cl), __int_as_float(cr), 0.f, 0.f);
+    nodes[4 * (size_t)i + 3] = n3;
+    int t = top_id[i];
+    if (t >= 0) {
+        top[4 * t + 0] = nodes[4 * (size_t)i + 0];
+        top[4 * t + 1] = nodes[4 * (size_t)i + 1];
+        top[4 * t + 2] = nodes[4 * (size_t)i + 2];
+        top[4 * t + 3] = n3;
+    }
+}
+
+inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct TempLayout {
+    size_t box_lo, box_hi, keys_a, keys_b, vals_a, vals_b, children, parent_node, parent_leaf, flags, node_lo, node_hi,
+        top_id, order, bounds, meta, cub, total, cub_bytes;
+};
+
+TempLayout layout(int n) {
+    TempLayout L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    size_t m = (size_t)(n > 1 ? n - 1 : 1);
+    L.box_lo = take(16 * (size_t)n); L.box_hi = take(16 * (size_t)n);
+    L.keys_a = take(4 * (size_t)n); L.keys_b = take(4 * (size_t)n);
+    L.vals_a = take(4 * (size_t)n); L.vals_b = take(4 * (size_t)n);
+    L.children = take(8 * m); L.parent_node = take(4 * m); L.parent_leaf = take(4 * (size_t)n);
+    L.flags = take(4 * m); L.node_lo = take(16 * m); L.node_hi = take(16 * m);
+    L.top_id = take(4 * m); L.order = take(4 * 4096); L.bounds = take(32); L.meta = take(32);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int *)nullptr, (int *)nullptr, n, 0, 30);
+    L.cub_bytes = cub_bytes;
+    L.cub = take(cub_bytes);
+    L.total = off;
+    return L;
+}
+
+}  // namespace
+
+size_t lbvh_temp_bytes(int n_prims) { return layout(n_prims > 0 ? n_prims : 1).total; }
+
+cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, const float4 *sphere, const float4 *tri,
+                       float pad, float4 *nodes, float4 *top, int top_capacity, int *h_meta, void *temp,
+                       size_t temp_bytes, cudaStream_t stream) {
+    int n = n_rect + n_sphere + n_tri;
+    h_meta[0] = 0; h_meta[1] = -1; h_meta[2] = 0;
+    if (n <= 0) { h_meta[1] = 0; return cudaSuccess; }
+    if (n == 1) { h_meta[1] = ~0; return cudaSuccess; }        // a single leaf: root = ~prim 0
+    TempLayout L = layout(n);
+    if (temp_bytes < L.total) return cudaErrorInvalidValue;
+    if (top_capacity > 4096) top_capacity = 4096;
+    char *base = (char *)temp;
+    float4 *box_lo = (float4 *)(base + L.box_lo), *box_hi = (float4 *)(base + L.box_hi);
+    uint32_t *keys_a = (uint32_t *)(base + L.keys_a), *keys_b = (uint32_t *)(base + L.keys_b);
+    int *vals_a = (int *)(base + L.vals_a), *vals_b = (int *)(base + L.vals_b);
+    int2 *children = (int2 *)(base + L.children);
+    int *parent_node = (int *)(base + L.parent_node), *parent_leaf = (int *)(base + L.parent_leaf);
+    int *flags = (int *)(base + L.flags);
+    float4 *node_lo = (float4 *)(base + L.node_lo), *node_hi = (float4 *)(base + L.node_hi);
+    int *top_id = (int *)(base + L.top_id), *order = (int *)(base + L.order);
+    int *bounds = (int *)(base + L.bounds), *meta = (int *)(base + L.meta);
+
+    const int T = 256, G = (n + T - 1) / T;
+    // scene centroid bounds start at (+max, -max) in the ordered-int encoding
+    int init[8] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000, 0, 0};
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(bounds, init, sizeof init, cudaMemcpyHostToDevice, stream))) return e;
+    if ((e = cudaMemsetAsync(flags, 0, 4 * (size_t)(n - 1), stream))) return e;
+    if ((e = cudaMemsetAsync(top_id, 0xff, 4 * (size_t)(n - 1), stream))) return e;
+    if ((e = cudaMemsetAsync(meta, 0, 32, stream))) return e;
+    bounds_kernel<<<G, T, 0, stream>>>(n, n_rect, n_sphere, rect, sphere, tri, pad, box_lo, box_hi, bounds);
+    morton_kernel<<<G, T, 0, stream>>>(n, box_lo, box_hi, bounds, keys_a, vals_a);
+    size_t cub_bytes = L.cub_bytes;
+    if ((e = cub::DeviceRadixSort::SortPairs(base + L.cub, cub_bytes, keys_a, keys_b, vals_a, vals_b, n, 0, 30, stream)))
+        return e;
+    hierarchy_kernel<<<G, T, 0, stream>>>(n, keys_b, vals_b, children, parent_node, parent_leaf);
+    refit_kernel<<<G, T, 0, stream>>>(n, children, parent_node, parent_leaf, box_lo, box_hi, flags, node_lo, node_hi, nodes);
+    top_order_kernel<<<1, 1024, 0, stream>>>(n - 1, children, top_capacity, top_id, order, meta);
+    finalize_kernel<<<(n - 1 + T - 1) / T, T, 0, stream>>>(n - 1, top_id, meta, nodes, top);
+    if ((e = cudaGetLastError())) return e;
+    int hm[8];
+    if ((e = cudaMemcpyAsync(hm, meta, 32, cudaMemcpyDeviceToHost, stream))) return e;
+    if ((e = cudaStreamSynchronize(stream))) return e;
+    h_meta[0] = hm[0]; h_meta[1] = hm[1]; h_meta[2] = hm[2];
+    return cudaSuccess;
+}
+
+}  // namespace b2rt

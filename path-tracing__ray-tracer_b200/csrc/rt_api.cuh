@@ -1,0 +1,175 @@
+// rt_api.cuh — implementation of the launchers declared in rt_api.h (included by rt_f32.cu / rt_f64.cu).
+#pragma once
+#include <type_traits>
+
+#include "rt_api.h"
+#include "rt_path.cuh"
+#include "rt_whitted.cuh"
+
+namespace b2rt {
+
+
+inline size_t smem_top_bytes(const SceneDev &S) { return (size_t)S.n_top * 64; }
+
+inline int persistent_grid(const void *kernel, int block, size_t smem) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+template <typename R>
+cudaError_t Api<R>::primary_hits(const b2rt_scene *s, const double *cam, int W, int H, double du, double dv,
+                                 double t_min, double t_max, int use_bvh, int *ids, double *tt, cudaStream_t st) {
+    SceneDev S = make_scene_dev(s);
+    Cam<R> c = make_cam<R>(cam);
+    int n = W * H, T = 128;
+    if (S.semantics == B2RT_SEM_CPU)
+        primary_hits_kernel<R, true><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, R(du), R(dv), R(t_min), R(t_max), use_bvh, ids, tt);
+    else
+        primary_hits_kernel<R, false><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, R(du), R(dv), R(t_min), R(t_max), use_bvh, ids, tt);
+    return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Api<R>::trace_rays(const b2rt_scene *s, int n, const double *o, const double *d, double t_min, double t_max,
+                               int any_hit, int use_bvh, int *ids, double *rec, cudaStream_t st) {
+    SceneDev S = make_scene_dev(s);
+    int T = 128;
+    if (n <= 0) return cudaSuccess;
+    if (S.semantics == B2RT_SEM_CPU)
+        trace_rays_kernel<R, true><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, n, o, d, R(t_min), R(t_max), any_hit, use_bvh, ids, rec);
+    else
+        trace_rays_kernel<R, false><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, n, o, d, R(t_min), R(t_max), any_hit, use_bvh, ids, rec);
+    return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Api<R>::whitted_cpu(const b2rt_scene *s, const double *cam, int W, int H, const double *jitter,
+                                int max_depth, const double *ambient, const double *light_color, double *rgb,
+                                cudaStream_t st) {
+    SceneDev S = make_scene_dev(s);
+    Cam<R> c = make_cam<R>(cam);
+    V3<R> amb = {R(ambient[0]), R(ambient[1]), R(ambient[2])};
+    V3<R> lc = {R(light_color[0]), R(light_color[1]), R(light_color[2])};
+    int n = W * H, T = 128;
+    whitted_cpu_kernel<R><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, jitter, max_depth, amb, lc, rgb);
+    return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Api<R>::whitted_texture(const b2rt_scene *s, const double *cam, int W, int H, int spp, int max_depth,
+                                    double *rgb, uint8_t *u8, cudaStream_t st) {
+    SceneDev S = make_scene_dev(s);
+    Cam<R> c = make_cam<R>(cam);
+    int n = W * H, T = 128;
+    whitted_texture_kernel<R><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, spp, max_depth, rgb, u8);
+    return cudaGetLastError();
+}
+
+// ---- wavefront path tracer --------------------------------------------------------------------
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+template <typename R> struct PathLayout {
+    size_t stream_bytes, counts_off, total;
+    static PathLayout make(int W, int H, int spp_per_wave, int max_depth) {
+        PathLayout L;
+        size_t n = (size_t)W * H * spp_per_wave;
+        L.stream_bytes = align256(n * sizeof(real4<R>));
+        L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
+        L.total = L.counts_off + align256(sizeof(int) * (2 * (size_t)max_depth + 2) + 16);
+        return L;
+    }
+};
+
+template <typename R> size_t Api<R>::path_workspace_bytes(int W, int H, int spp_per_wave, int max_depth) {
+    return PathLayout<R>::make(W, H, spp_per_wave, max_depth).total;
+}
+
+template <typename R, typename Rng>
+cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathArgs &a, cudaStream_t st) {
+    SceneDev S = make_scene_dev(s);
+    Cam<R> c = make_cam<R>(cam);
+    const int W = a.width, H = a.height, npix = W * H;
+    int wave = a.spp_per_wave < 1 ? 1 : a.spp_per_wave;
+    if (wave > a.spp_local) wave = a.spp_local;
+    if (a.spp_local <= 0) return cudaSuccess;
+    PathLayout<R> L = PathLayout<R>::make(W, H, wave, a.max_depth);
+    if (a.workspace_bytes < L.total) return cudaErrorInvalidValue;
+    char *base = (char *)a.workspace;
+    PathQueues<R> Q;
+    auto stream_at = [&](int k) { return (real4<R> *)(base + (size_t)k * L.stream_bytes); };
+    Q.ro[0] = stream_at(0); Q.rd[0] = stream_at(1); Q.th[0] = stream_at(2);
+    Q.ro[1] = stream_at(3); Q.rd[1] = stream_at(4); Q.th[1] = stream_at(5);
+    Q.hit = stream_at(6); Q.so = stream_at(7); Q.sd = stream_at(8); Q.sc = stream_at(9); Q.L = stream_at(10);
+    int *counts = (int *)(base + L.counts_off);
+    Q.ray_count = counts;
+    Q.shadow_count = counts + a.max_depth + 1;
+    Q.unshadowed = (unsigned long long *)(counts + 2 * (a.max_depth + 1));   // even int count: 8-byte aligned
+    size_t counts_bytes = sizeof(int) * 2 * ((size_t)a.max_depth + 1) + 8;
+
+    const size_t smem = smem_top_bytes(S);
+    const int T = 256;
+    static int g_extend = 0, g_shade = 0, g_shadow = 0, g_simple = 0;
+    // persistent grids: resident CTAs per SM x SM count (a multiple of the 148 SMs)
+    g_extend = persistent_grid((const void *)extend_kernel<R>, T, smem);
+    g_shade = persistent_grid((const void *)shade_kernel<R, Rng>, T, 0);
+    g_shadow = persistent_grid((const void *)shadow_kernel<R>, T, smem);
+    g_simple = persistent_grid((const void *)accumulate_kernel<R>, T, 0);
+
+    if (std::is_same<Rng, RefRng>::value) {
+        if (!a.pixel_rng) return cudaErrorInvalidValue;
+        init_pixel_rng_kernel<<<(npix + 255) / 256, 256, 0, st>>>(W, H, (long long)a.seed, a.sample_offset, a.pixel_rng);
+    }
+    cudaError_t e;
+    for (int done = 0; done < a.spp_local; done += wave) {
+        int k = a.spp_local - done < wave ? a.spp_local - done : wave;
+        unsigned long long launches = 0;
+        if ((e = cudaMemsetAsync(counts, 0, counts_bytes, st))) return e;
+        prof_begin(kRaygen, st);
+        raygen_kernel<R, Rng><<<g_simple, T, 0, st>>>(c, W, H, k, a.sample_offset + done, a.seed, a.pixel_rng, Q);
+        prof_end(st);
+        ++launches;
+        int buf = 0;
+        for (int b = 0; b < a.max_depth; ++b) {
+            prof_begin(kExtend, st);
+            extend_kernel<R><<<g_extend, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.ray_count + b);
+            prof_end(st);
+            prof_begin(kShade, st);
+            shade_kernel<R, Rng><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth);
+            prof_end(st);
+            prof_begin(kShadow, st);
+            shadow_kernel<R><<<g_shadow, T, smem, st>>>(S, Q, b);
+            prof_end(st);
+            launches += 3;
+            buf ^= 1;
+        }
+        prof_begin(kAccumulate, st);
+        accumulate_kernel<R><<<g_simple, T, 0, st>>>(npix, k, Q.L, (real4<R> *)a.accum);
+        prof_end(st);
+        ++launches;
+        if (a.counters) {
+            path_counters_kernel<<<1, 1, 0, st>>>(Q.ray_count, Q.shadow_count, Q.unshadowed, a.max_depth,
+                                                  (long long)npix * k, launches + 1, a.counters);
+        }
+        if ((e = cudaGetLastError())) return e;
+    }
+    return cudaSuccess;
+}
+
+template <typename R>
+cudaError_t Api<R>::render_path(const b2rt_scene *s, const double *cam, const PathArgs &a, cudaStream_t st) {
+    if (a.rng_mode == B2RT_RNG_REFERENCE) return render_path_impl<R, RefRng>(s, cam, a, st);
+    return render_path_impl<R, PcgRng>(s, cam, a, st);
+}
+
+template <typename R>
+cudaError_t Api<R>::resolve(const void *accum, int W, int H, double spp, int tonemap, uint8_t *u8, cudaStream_t st) {
+    int n = W * H;
+    resolve_kernel<R><<<(n + 255) / 256, 256, 0, st>>>((const real4<R> *)accum, W, H, R(spp), tonemap, u8);
+    return cudaGetLastError();
+}
+
+}  // namespace b2rt

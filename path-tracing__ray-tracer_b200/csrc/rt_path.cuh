@@ -1,0 +1,340 @@
+// rt_path.cuh — the wavefront path tracer (replaces cuda_path_trace_kernel + cuda_trace_path,
+// renderers/cuda_path_tracer.py:17-471).
+//
+// One WAVE = spp_per_wave samples of every pixel.  Path state lives in compacted HBM queues of real4
+// record streams; each bounce is three persistent grid-stride kernels:
+//     extend  : ray queue  -> closest hit (LBVH walk, top levels in shared memory)   -> hit stream
+//     shade   : ray+hit    -> texture, NEE shadow ray, Russian roulette, BSDF sample  -> next ray queue
+//                             (warp-ballot / prefix-popcount compaction, one atomic per warp per queue)
+//     shadow  : shadow queue -> occlusion query -> per-path radiance
+// Queue record streams (16 B * 3 per path for float):
+//     ro = (origin.xyz, slot)   rd = (direction.xyz, rng state)   th = (throughput.rgb, depth)
+// Shadow records: so = (origin.xyz, slot)  sd = (direction.xyz, -)  sc = (throughput*contribution.rgb, -)
+// slot = s_local * n_pixels + pixel indexes the per-path radiance L[slot] (never compacted), which makes
+// every radiance update a race-free plain read-modify-write and the per-pixel sum order deterministic.
+#pragma once
+#include <type_traits>
+
+#include "rt_scene.cuh"
+
+namespace b2rt {
+
+// ------------------------------------------------------------------------------------ RNG policies
+// random(state) is a pure function of the state and advance(state) steps it — the reference's
+// calling convention (cuda_random / cuda_xorshift, cuda_path_tracer.py:61-71), which the integrator
+// below follows draw for draw.
+struct RefRng {                       // the reference's generator, int64 arithmetic
+    static __device__ __forceinline__ uint64_t advance(uint64_t s) {
+        long long x = (long long)s;
+        x ^= (long long)((unsigned long long)x << 13);
+        x ^= x >> 17;                                          // arithmetic shift of the 64-bit value
+        x ^= (long long)((unsigned long long)x << 5);
+        return (uint64_t)(x & 0xffffffffLL);
+    }
+    template <typename R> static __device__ __forceinline__ R random(uint64_t s) {
+        return R((double)(s & 0xffffffULL) / 16777216.0);
+    }
+};
+struct PcgRng {                       // 32-bit PCG-RXS-M-XS stream, seeded by hashing (pixel, sample, seed)
+    static __device__ __forceinline__ uint64_t advance(uint64_t s) {
+        return (uint64_t)((uint32_t)s * 747796405u + 2891336453u);
+    }
+    template <typename R> static __device__ __forceinline__ R random(uint64_t s64) {
+        uint32_t s = (uint32_t)s64;
+        uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+        w = (w >> 22u) ^ w;
+        return R(w >> 8) * R(1.0 / 16777216.0);
+    }
+    static __device__ __forceinline__ uint32_t mix(uint32_t h) {
+        h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+        return h;
+    }
+    static __device__ __forceinline__ uint64_t seed(uint32_t pixel, uint64_t sample, uint64_t seed) {
+        uint32_t h = mix(pixel * 0x9e3779b1u + (uint32_t)seed);
+        h = mix(h ^ ((uint32_t)sample * 0x85ebca77u + (uint32_t)(seed >> 32)));
+        h = mix(h + (uint32_t)(sample >> 32) * 0xc2b2ae3du + 0x27d4eb2fu);
+        return (uint64_t)h;
+    }
+};
+
+template <typename R> struct PathQueues {
+    real4<R> *ro[2], *rd[2], *th[2];      // double-buffered ray queue streams
+    real4<R> *hit;                         // (t, prim, a, b)
+    real4<R> *so, *sd, *sc;                // shadow queue streams
+    real4<R> *L;                           // per-path radiance
+    int *ray_count;                        // [max_depth + 1]
+    int *shadow_count;                     // [max_depth]
+    unsigned long long *unshadowed;        // [1]
+};
+
+// ------------------------------------------------------------------------------------ raygen
+// cuda_path_trace_kernel's sample loop (:28-46).  One thread per pixel walks its spp_wave samples so
+// the reference generator's per-pixel sequential state can be carried in pixel_rng.
+template <typename R, typename Rng>
+__global__ void __launch_bounds__(256)
+raygen_kernel(Cam<R> cam, int W, int H, int spp_wave, long long first_sample, unsigned long long seed,
+              long long *pixel_rng, PathQueues<R> Q) {
+    int npix = W * H;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        int x = pix % W, y = pix / W;
+        uint64_t state = 0;
+        if constexpr (std::is_same<Rng, RefRng>::value) state = (uint64_t)pixel_rng[pix];
+        for (int s = 0; s < spp_wave; ++s) {
+            if constexpr (std::is_same<Rng, PcgRng>::value)
+                state = PcgRng::seed((uint32_t)pix, (uint64_t)(first_sample + s), seed);
+            R rnd = Rng::template random<R>(state);          // :35-36 the same draw jitters u and v
+            R u = (R(x) + rnd) / R(W), v = (R(y) + rnd) / R(H);
+            state = Rng::advance(state);                      // :37
+            Ray<R> r = camera_ray<R>(cam, u, v);
+            size_t i = (size_t)s * npix + pix;
+            Q.ro[0][i] = Real4<R>::make(r.o.x, r.o.y, r.o.z, pack_int<R>((int64_t)i));
+            Q.rd[0][i] = Real4<R>::make(r.d.x, r.d.y, r.d.z, pack_int<R>((int64_t)state));   // by value (:40-41)
+            Q.th[0][i] = Real4<R>::make(R(1), R(1), R(1), pack_int<R>(0));
+            Q.L[i] = Real4<R>::make(R(0), R(0), R(0), R(0));
+            if constexpr (std::is_same<Rng, RefRng>::value) state = Rng::advance(state);     // :46
+        }
+        if constexpr (std::is_same<Rng, RefRng>::value) pixel_rng[pix] = (long long)state;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) Q.ray_count[0] = npix * spp_wave;
+}
+
+// reference generator: seed every pixel (:28) and skip 2*first_sample steps (two advances per sample)
+static __global__ void init_pixel_rng_kernel(int W, int H, long long frame_count, long long first_sample, long long *pixel_rng) {
+    int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= W * H) return;
+    long long s = ((long long)pix + frame_count * W * H) * 1103515245LL + 12345LL;
+    uint64_t st = (uint64_t)s;
+    for (long long k = 0; k < 2 * first_sample; ++k) st = RefRng::advance(st);
+    pixel_rng[pix] = (long long)st;
+}
+
+// ------------------------------------------------------------------------------------ extend
+template <typename R>
+__global__ void __launch_bounds__(256)
+extend_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__restrict__ rd,
+              real4<R> *__restrict__ hit, const int *__restrict__ count) {
+    extern __shared__ float4 s_top[];
+    stage_top(S, s_top);
+    int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        real4<R> a = ro[i], b = rd[i];
+        Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
+        Hit<R> h;
+        traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
+        hit[i] = Real4<R>::make(h.t, pack_int<R>((int64_t)h.prim), h.a, h.b);
+    }
+}
+
+// cuda_sample_hemisphere_cosine (:139-180)
+template <typename R, typename Rng>
+__device__ __forceinline__ V3<R> cos_hemisphere(V3<R> n, uint64_t &rng) {
+    R r1 = Rng::template random<R>(rng); rng = Rng::advance(rng);
+    R r2 = Rng::template random<R>(rng); rng = Rng::advance(rng);
+    R ct = sqrt_(r1), st = sqrt_(R(1) - r1);
+    R sp, cp;
+    if constexpr (sizeof(R) == 4) sincospif(2.0f * r2, &sp, &cp);
+    else { R phi = R(2.0) * R(3.141592653589793) * r2; sp = sin(phi); cp = cos(phi); }
+    R x = st * cp, y = st * sp, z = ct;
+    V3<R> t = abs_(n.z) > R(0.9) ? V3<R>{R(1), R(0), R(0)} : V3<R>{R(0), R(0), R(1)};
+    V3<R> u = {t.y * n.z - t.z * n.y, t.z * n.x - t.x * n.z, t.x * n.y - t.y * n.x};
+    R ul = length(u);
+    u = u / ul;
+    V3<R> v = {n.y * u.z - n.z * u.y, n.z * u.x - n.x * u.z, n.x * u.y - n.y * u.x};
+    return {x * u.x + y * v.x + z * n.x, x * u.y + y * v.y + z * n.y, x * u.z + y * v.z + z * n.z};
+}
+
+// warp-aggregated queue append: one atomicAdd per warp, slots handed out by prefix popcount
+__device__ __forceinline__ int warp_append(int *counter, bool want) {
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return -1;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return want ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// ------------------------------------------------------------------------------------ shade
+// One loop iteration of cuda_trace_path (:229-469) for every queued path.
+template <typename R, typename Rng>
+__global__ void __launch_bounds__(256)
+shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth) {
+    const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
+    real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
+    int n = Q.ray_count[bounce];
+    int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool valid = i < n;
+        bool alive = false, want_shadow = false;
+        V3<R> new_o, new_d, thr, s_o, s_d, s_c;
+        uint64_t rng = 0;
+        int slot = 0;
+        if (valid) {
+            real4<R> a = ro[i], b = rd[i], c = th[i], hrec = Q.hit[i];
+            Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
+            slot = (int)unpack_u<R>(a.w);
+            rng = unpack_u<R>(b.w);
+            thr = xyz<R>(c);
+            Hit<R> h; h.t = hrec.x; h.prim = (int)(long long)real_as_int(hrec.y); h.a = hrec.z; h.b = hrec.w;
+            if (h.prim < 0) {                                                       // :234-239 sky
+                real4<R> l = Q.L[slot];
+                Q.L[slot] = Real4<R>::make(l.x + thr.x * R(0.1), l.y + thr.y * R(0.1), l.z + thr.z * R(0.1), l.w);
+            } else {
+                Surface<R> sf;
+                make_surface<R, false>(S, r, h, sf);
+                V3<R> mc = base_color<R, false>(S, sf);
+                V3<R> po = sf.p + sf.n * R(0.001);
+                if (S.n_lights > 0) {                                               // :265-304
+                    R nl = R(S.n_lights);
+                    int li = (int)(Rng::template random<R>(rng) * nl);
+                    if (li >= S.n_lights) li = S.n_lights - 1;
+                    rng = Rng::advance(rng);
+                    V3<R> l = xyz<R>(ldg4(reinterpret_cast<const real4<R> *>(S.lights) + li)) - sf.p;
+                    R dist = length(l);
+                    if (dist > R(0.001)) l = l / dist;
+                    R pdf = R(1) / nl;
+                    R ct = max_(R(0), l.x * sf.n.x + l.y * sf.n.y + l.z * sf.n.z);
+                    R li_, lm;
+                    if (sf.refractive > R(0.5)) { li_ = R(4.0); lm = R(0.6); }
+                    else if (sf.reflective > R(0.7)) { li_ = R(2.5); lm = R(0.8); }
+                    else { li_ = R(2.0); lm = R(1.0); }
+                    s_c = {thr.x * (mc.x * sf.diffuse * ct * li_ * lm / pdf),
+                           thr.y * (mc.y * sf.diffuse * ct * li_ * lm / pdf),
+                           thr.z * (mc.z * sf.diffuse * ct * li_ * lm / pdf)};
+                    // a shadow ray whose payload is exactly zero cannot change the image: not queued
+                    want_shadow = (s_c.x != R(0)) || (s_c.y != R(0)) || (s_c.z != R(0));
+                    s_o = po; s_d = l;
+                }
+                bool go = true;
+                if (bounce >= 3) {                                                  // :307-314
+                    R p = max_(R(0.1), R(0.299) * thr.x + R(0.587) * thr.y + R(0.114) * thr.z);
+                    if (Rng::template random<R>(rng) > p) go = false;
+                    else { rng = Rng::advance(rng); thr = thr / p; }
+                }
+                if (go) {
+                    R choice = Rng::template random<R>(rng);                        // :317-318
+                    rng = Rng::advance(rng);
+                    R dn = r.d.x * sf.n.x + r.d.y * sf.n.y + r.d.z * sf.n.z;
+                    V3<R> refl = {r.d.x - R(2) * dn * sf.n.x, r.d.y - R(2) * dn * sf.n.y, r.d.z - R(2) * dn * sf.n.z};
+                    new_o = po;
+                    if (sf.refractive > R(0.1)) {                                   // :320-428 glass
+                        if (choice < R(0.6)) {
+                            R cos_i = max_(R(0), -dn);
+                            bool entering = cos_i > R(0);
+                            V3<R> on = entering ? sf.n : -sf.n;
+                            R eta = entering ? R(1) / sf.ior : sf.ior;
+                            V3<R> rr;
+                            if (refract_nb<R>(r.d, on, eta, rr)) {
+                                if (entering) new_o = sf.p - sf.n * R(0.001);
+                                new_d = rr;
+                                thr = thr * (sf.refractive / R(0.6));
+                            } else { new_d = refl; thr = thr * R(0.9); }
+                        } else if (choice < R(0.6) + R(0.25)) {
+                            new_d = refl;
+                            thr = {thr.x * (mc.x * R(0.9) / R(0.25)), thr.y * (mc.y * R(0.9) / R(0.25)),
+                                   thr.z * (mc.z * R(0.9) / R(0.25))};
+                        } else {
+                            new_d = cos_hemisphere<R, Rng>(sf.n, rng);
+                            thr = {thr.x * (mc.x * sf.diffuse * R(3.0) / R(0.15)), thr.y * (mc.y * sf.diffuse * R(3.0) / R(0.15)),
+                                   thr.z * (mc.z * sf.diffuse * R(3.0) / R(0.15))};
+                        }
+                    } else if (sf.reflective > R(0.5)) {                            // :430-449 mirror
+                        new_d = refl;
+                        thr = {thr.x * (mc.x * sf.reflective), thr.y * (mc.y * sf.reflective), thr.z * (mc.z * sf.reflective)};
+                    } else {                                                        // :451-466 diffuse
+                        new_d = cos_hemisphere<R, Rng>(sf.n, rng);
+                        thr = {thr.x * (mc.x * sf.diffuse), thr.y * (mc.y * sf.diffuse), thr.z * (mc.z * sf.diffuse)};
+                    }
+                    alive = !(max_(thr.x, max_(thr.y, thr.z)) < R(0.001))           // :468
+                            && (bounce + 1 < max_depth);                            // :229 loop bound
+                }
+            }
+        }
+        int si = warp_append(Q.shadow_count + bounce, want_shadow);
+        if (want_shadow) {
+            Q.so[si] = Real4<R>::make(s_o.x, s_o.y, s_o.z, pack_int<R>((int64_t)slot));
+            Q.sd[si] = Real4<R>::make(s_d.x, s_d.y, s_d.z, R(0));
+            Q.sc[si] = Real4<R>::make(s_c.x, s_c.y, s_c.z, R(0));
+        }
+        int ni = warp_append(Q.ray_count + bounce + 1, alive);
+        if (alive) {
+            no[ni] = Real4<R>::make(new_o.x, new_o.y, new_o.z, pack_int<R>((int64_t)slot));
+            nd[ni] = Real4<R>::make(new_d.x, new_d.y, new_d.z, pack_int<R>((int64_t)rng));
+            nt[ni] = Real4<R>::make(thr.x, thr.y, thr.z, pack_int<R>((int64_t)(bounce + 1)));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ shadow
+template <typename R>
+__global__ void __launch_bounds__(256)
+shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
+    extern __shared__ float4 s_top[];
+    stage_top(S, s_top);
+    int n = Q.shadow_count[bounce];
+    int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool lit = false;
+        if (i < n) {
+            real4<R> a = Q.so[i], b = Q.sd[i];
+            Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
+            Hit<R> h;
+            lit = !traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);   // :275-277 t_max = 1e6
+            if (lit) {
+                int slot = (int)unpack_u<R>(a.w);
+                real4<R> c = Q.sc[i], l = Q.L[slot];
+                Q.L[slot] = Real4<R>::make(l.x + c.x, l.y + c.y, l.z + c.z, l.w);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, lit);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(Q.unshadowed, (unsigned long long)__popc(m));
+    }
+}
+
+// ------------------------------------------------------------------------------------ accumulate / resolve
+// per-pixel radiance accumulation: accum[pix] += sum_s L[s][pix], samples in index order (:43-45)
+template <typename R>
+__global__ void __launch_bounds__(256)
+accumulate_kernel(int npix, int spp_wave, const real4<R> *__restrict__ L, real4<R> *__restrict__ accum) {
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        // wave-local partial sum first: the float32 running sum then sees one add per wave, not per sample
+        R sx = R(0), sy = R(0), sz = R(0);
+        for (int s = 0; s < spp_wave; ++s) {
+            real4<R> l = L[(size_t)s * npix + pix];
+            sx += l.x; sy += l.y; sz += l.z;
+        }
+        real4<R> a = accum[pix];
+        a.x += sx; a.y += sy; a.z += sz;
+        accum[pix] = a;
+    }
+}
+
+static __global__ void path_counters_kernel(const int *ray_count, const int *shadow_count, const unsigned long long *unshadowed,
+                                     int max_depth, long long paths, unsigned long long launches,
+                                     unsigned long long *out) {
+    unsigned long long rays = 0, shadows = 0;
+    for (int b = 0; b < max_depth; ++b) { rays += (unsigned)ray_count[b]; shadows += (unsigned)shadow_count[b]; }
+    out[0] += (unsigned long long)paths; out[1] += rays; out[2] += shadows; out[3] += *unshadowed; out[4] += launches;
+}
+
+// mean -> ACES (cuda_tonemap :74-81) -> min(255, max(0, int(c*255))) (:56-58) -> V flip (:807)
+template <typename R>
+__global__ void __launch_bounds__(256)
+resolve_kernel(const real4<R> *__restrict__ accum, int W, int H, R spp, int tonemap, uint8_t *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    int x = i % W, y = i / W;
+    real4<R> a = accum[i];
+    R c[3] = {a.x / spp, a.y / spp, a.z / spp};
+    uint8_t *o = out + 3 * ((size_t)(H - 1 - y) * W + x);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        R v = c[k];
+        if (tonemap) v = (v * (R(2.51) * v + R(0.03))) / (v * (R(2.43) * v + R(0.59)) + R(0.14));
+        long long q = (long long)(v * R(255));
+        o[k] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    }
+}
+
+}  // namespace b2rt

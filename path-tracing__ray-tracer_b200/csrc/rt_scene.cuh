@@ -1,0 +1,350 @@
+// rt_scene.cuh — device scene view, primitive intersection and stack-based LBVH traversal.
+//
+// Reference functions restated here (operation order kept so that the float64 instantiation,
+// compiled with -fmad=false, reproduces the reference's float64 results bit for bit):
+//   rectangle : Plane.hit      core/geometry.py:50-72     / cuda_scene_hit :511-574
+//   sphere    : Sphere.hit     core/geometry.py:85-111    / cuda_scene_hit :582-631
+//   triangle  : Triangle.hit   core/geometry.py:139-171   / cuda_scene_hit :639-728
+//   closest   : BVHNode.hit / Scene.hit (core/acceleration.py:32-40) replaced by an LBVH walk whose
+//               result equals the brute-force scan's: min t, ties -> lowest packed id.
+#pragma once
+#include "rt_math.cuh"
+#include "rt_api.h"
+
+namespace b2rt {
+
+constexpr int kStackDepth = 64;       // LBVH depth bound: 30 Morton bits + log2(duplicates)
+
+struct SceneDev {
+    int n_rect, n_sphere, n_tri, n_prims;
+    int n_mat, n_tex, n_lights;
+    int semantics;
+    const void *rect, *sphere, *tri, *shade, *mat, *lights;
+    const int *prim_mat, *mat_tex;
+    const uint32_t *texels;
+    const int4 *tex_info;
+    const float4 *nodes, *top;
+    int n_top, root;
+};
+
+inline SceneDev make_scene_dev(const b2rt_scene *s) {
+    SceneDev d;
+    d.n_rect = s->n_rect; d.n_sphere = s->n_sphere; d.n_tri = s->n_tri;
+    d.n_prims = s->n_rect + s->n_sphere + s->n_tri;
+    d.n_mat = s->n_mat; d.n_tex = s->n_tex; d.n_lights = s->n_lights;
+    d.semantics = s->semantics;
+    d.rect = s->d_rect; d.sphere = s->d_sphere; d.tri = s->d_tri; d.shade = s->d_shade;
+    d.mat = s->d_mat; d.lights = s->d_lights;
+    d.prim_mat = s->d_prim_mat; d.mat_tex = s->d_mat_tex;
+    d.texels = s->d_texels; d.tex_info = reinterpret_cast<const int4 *>(s->d_tex_info);
+    d.nodes = reinterpret_cast<const float4 *>(s->d_bvh_nodes);
+    d.top = reinterpret_cast<const float4 *>(s->d_bvh_top);
+    d.n_top = s->n_bvh_top; d.root = s->bvh_root;
+    return d;
+}
+
+// closest-hit record: a/b are (u_hit, v_hit) in world units for a rectangle, the barycentrics
+// (u, v) for a triangle, unused for a sphere
+template <typename R> struct Hit {
+    R t, a, b;
+    int prim;
+};
+
+template <typename R> struct Ray {
+    V3<R> o, d;
+};
+
+// ---------------------------------------------------------------------------------- primitives
+// Every test returns true and fills (t, a, b) when the primitive is hit inside the open interval
+// (t_min, t_far); the caller applies the tie rule.  CPU semantics: Plane accepts the closed range.
+
+template <typename R, bool CpuSem>
+__device__ __forceinline__ bool hit_rect(const SceneDev &S, int i, const Ray<R> &r, R t_min, R t_far, bool allow_eq,
+                                         R &t_out, R &a_out, R &b_out) {
+    const real4<R> *q = reinterpret_cast<const real4<R> *>(S.rect) + 4 * i;
+    real4<R> r0 = ldg4(q), r1 = ldg4(q + 1);
+    V3<R> anchor = xyz<R>(r0), n = xyz<R>(r1);
+    R denom = dot(n, r.d);
+    if (CpuSem ? (abs_(denom) < R(1e-6)) : !(abs_(denom) > R(1e-6))) return false;
+    R t = dot(anchor - r.o, n) / denom;
+    if (CpuSem) {                                            // closed range (core/geometry.py:56)
+        if (t < t_min || !(t < t_far || (allow_eq && t == t_far))) return false;
+    } else {
+        if (!(t_min < t && (t < t_far || (allow_eq && t == t_far)))) return false;
+    }
+    real4<R> r2 = ldg4(q + 2), r3 = ldg4(q + 3);
+    V3<R> p = r.o + r.d * t;
+    V3<R> rel = p - anchor;
+    R uh = dot(rel, xyz<R>(r2)), vh = dot(rel, xyz<R>(r3));
+    if (!(R(0) <= uh && uh <= r0.w && R(0) <= vh && vh <= r1.w)) return false;
+    t_out = t; a_out = uh; b_out = vh;
+    return true;
+}
+
+template <typename R>
+__device__ __forceinline__ bool hit_sphere(const SceneDev &S, int i, const Ray<R> &r, R t_min, R t_far, bool allow_eq,
+                                           R &t_out) {
+    const real4<R> *q = reinterpret_cast<const real4<R> *>(S.sphere) + 2 * i;
+    real4<R> s0 = ldg4(q);
+    V3<R> oc = r.o - xyz<R>(s0);
+    R a = dot(r.d, r.d);
+    R b = dot(oc, r.d);
+    R disc, r2;
+    if constexpr (sizeof(R) == 8) {
+        r2 = ldg4(q + 1).x;                                   // radius^2 as the reference rounds it
+        R c = dot(oc, oc) - r2;
+        disc = b * b - a * c;                                 // textbook half-b form (:601-606)
+    } else {
+        // float32: c = |oc|^2 - r^2 cancels catastrophically from 50 units away;
+        // b^2 - a*c == a * (r^2 - |oc - (b/a) d|^2) is the same quantity without the cancellation.
+        r2 = s0.w * s0.w;
+        V3<R> perp = oc - r.d * (b / a);
+        disc = a * (r2 - dot(perp, perp));
+    }
+    if (!(disc > R(0))) return false;
+    R sq = sqrt_(disc);
+    R t1 = (-b - sq) / a, t2 = (-b + sq) / a;
+    // nearest root beyond t_min, then the (t_min, t_far) range test — equals the reference's
+    // "t1 if in range else t2 if in range" because t2 > t1
+    R t;
+    if (t_min < t1) t = t1; else if (t_min < t2) t = t2; else return false;
+    if (!(t < t_far || (allow_eq && t == t_far))) {
+        // the reference falls through to t2 when t1 >= closest; t2 > t1 so it fails too
+        return false;
+    }
+    t_out = t;
+    return true;
+}
+
+template <typename R>
+__device__ __forceinline__ bool hit_tri(const SceneDev &S, int i, const Ray<R> &r, R t_min, R t_far, bool allow_eq,
+                                        R &t_out, R &u_out, R &v_out) {
+    const real4<R> *q = reinterpret_cast<const real4<R> *>(S.tri) + 3 * i;
+    V3<R> v0 = xyz<R>(ldg4(q)), e1 = xyz<R>(ldg4(q + 1)), e2 = xyz<R>(ldg4(q + 2));
+    V3<R> h = cross(r.d, e2);
+    R a = dot(e1, h);
+    if (abs_(a) < R(1e-6)) return false;
+    R f = R(1) / a;
+    V3<R> s = r.o - v0;
+    R u = f * dot(s, h);
+    if (u < R(0) || u > R(1)) return false;
+    V3<R> qq = cross(s, e1);
+    R v = f * dot(r.d, qq);
+    if (v < R(0) || u + v > R(1)) return false;
+    R t = f * dot(e2, qq);
+    if (!(t_min < t && (t < t_far || (allow_eq && t == t_far)))) return false;
+    t_out = t; u_out = u; v_out = v;
+    return true;
+}
+
+// Tests packed primitive `prim` and folds it into the running closest hit with the tie rule
+// "smaller t wins; equal t -> lower packed id" (the brute-force scan order of cuda_scene_hit).
+template <typename R, bool CpuSem>
+__device__ __forceinline__ void test_prim(const SceneDev &S, int prim, const Ray<R> &r, R t_min, Hit<R> &best) {
+    R t, a = R(0), b = R(0);
+    bool allow_eq;
+    if (CpuSem) {
+        // The reference BVH visits its leaves in scene.objects order (core/acceleration.py:20-26) and
+        // Plane.hit accepts t == t_max while Sphere/Triangle are strict (core/geometry.py:56,94,159):
+        // at equal t a later rectangle replaces anything, a later sphere/triangle replaces nothing.
+        bool cand_rect = prim < S.n_rect, best_rect = best.prim >= 0 && best.prim < S.n_rect;
+        if (best.prim < 0) allow_eq = cand_rect;             // t == t_max itself is inside a Plane's range
+        else allow_eq = cand_rect ? (!best_rect || prim > best.prim) : (!best_rect && prim < best.prim);
+    } else {
+        allow_eq = best.prim >= 0 && prim < best.prim;       // an equal-t hit may replace a higher id
+    }
+    bool ok;
+    if (prim < S.n_rect) ok = hit_rect<R, CpuSem>(S, prim, r, t_min, best.t, allow_eq, t, a, b);
+    else if (prim < S.n_rect + S.n_sphere) ok = hit_sphere<R>(S, prim - S.n_rect, r, t_min, best.t, allow_eq, t);
+    else ok = hit_tri<R>(S, prim - S.n_rect - S.n_sphere, r, t_min, best.t, allow_eq, t, a, b);
+    if (ok) { best.t = t; best.a = a; best.b = b; best.prim = prim; }
+}
+
+// ---------------------------------------------------------------------------------- traversal
+// LBVH node = 4 float4: child boxes + child references.
+//   n0 = (L.min.xyz, L.max.x)  n1 = (L.max.yz, R.min.xy)  n2 = (R.min.z, R.max.xyz)
+//   n3 = (bits(left ref), bits(right ref), -, -)     ref >= 0: node index (< n_top: in the smem copy),
+//                                                    ref <  0: leaf holding packed primitive ~ref
+// Boxes are float32, padded outward at build time; the slab test runs in R on the widened values.
+
+template <typename R>
+__device__ __forceinline__ bool slab(R bx0, R by0, R bz0, R bx1, R by1, R bz1, const V3<R> &o, const V3<R> &id,
+                                     R t_min, R t_far, R &t_enter) {
+    R tx0 = (bx0 - o.x) * id.x, tx1 = (bx1 - o.x) * id.x;
+    R ty0 = (by0 - o.y) * id.y, ty1 = (by1 - o.y) * id.y;
+    R tz0 = (bz0 - o.z) * id.z, tz1 = (bz1 - o.z) * id.z;
+    R tn = max_(max_(min_(tx0, tx1), min_(ty0, ty1)), max_(min_(tz0, tz1), t_min));
+    R tf = min_(min_(max_(tx0, tx1), max_(ty0, ty1)), min_(max_(tz0, tz1), t_far));
+    t_enter = tn;
+    return tn <= tf;
+}
+
+// Closest hit (AnyHit = false) or occlusion query (AnyHit = true) over (t_min, t_max).
+// s_top: shared-memory copy of S.top (may be nullptr when S.n_top == 0).
+template <typename R, bool CpuSem, bool AnyHit>
+__device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top, const Ray<R> &r, R t_min, R t_max,
+                                         Hit<R> &best) {
+    best.t = t_max; best.prim = -1; best.a = R(0); best.b = R(0);
+    if (S.n_prims == 0) return false;
+    V3<R> id = {R(1) / r.d.x, R(1) / r.d.y, R(1) / r.d.z};
+    int stack[kStackDepth];
+    int sp = 0;
+    int ref = S.root;
+    while (true) {
+        if (ref >= 0) {
+            float4 n0, n1, n2, n3;
+            if (ref < S.n_top) {
+                const float4 *p = s_top + 4 * ref;
+                n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+            } else {
+                const float4 *p = S.nodes + 4 * (size_t)(ref - S.n_top);
+                n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
+            }
+            R tl, tr;
+            // CPU semantics accept t == t_far on a rectangle, so boxes are tested against the closed range
+            bool hl = slab<R>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, r.o, id, t_min, best.t, tl);
+            bool hr = slab<R>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, r.o, id, t_min, best.t, tr);
+            int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+            if (hl && hr) {
+                bool swap = tr < tl;
+                stack[sp++] = swap ? cl : cr;
+                ref = swap ? cr : cl;
+            } else if (hl) {
+                ref = cl;
+            } else if (hr) {
+                ref = cr;
+            } else {
+                if (sp == 0) break;
+                ref = stack[--sp];
+            }
+        } else {
+            test_prim<R, CpuSem>(S, ~ref, r, t_min, best);
+            if (AnyHit && best.prim >= 0) return true;
+            if (sp == 0) break;
+            ref = stack[--sp];
+        }
+    }
+    return best.prim >= 0;
+}
+
+// brute-force scan in packed order (validation path; equals cuda_scene_hit's loop structure)
+template <typename R, bool CpuSem, bool AnyHit>
+__device__ __forceinline__ bool scan_all(const SceneDev &S, const Ray<R> &r, R t_min, R t_max, Hit<R> &best) {
+    best.t = t_max; best.prim = -1; best.a = R(0); best.b = R(0);
+    for (int p = 0; p < S.n_prims; ++p) {
+        test_prim<R, CpuSem>(S, p, r, t_min, best);
+        if (AnyHit && best.prim >= 0) return true;
+    }
+    return best.prim >= 0;
+}
+
+// cooperative copy of the BVH top levels into shared memory (call from every thread of the CTA)
+__device__ __forceinline__ void stage_top(const SceneDev &S, float4 *s_top) {
+    for (int i = threadIdx.x; i < 4 * S.n_top; i += blockDim.x) s_top[i] = __ldg(S.top + i);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------- surface
+template <typename R> struct Surface {
+    V3<R> p, n;            // hit point, shading normal as the reference defines it per primitive type
+    R u, v;                // texture coordinates
+    V3<R> color;           // material colour (before texturing)
+    R diffuse, specular, reflective, refractive, ior;
+    int tex;               // texture id or -1
+};
+
+// Rebuilds what cuda_scene_hit returns beside t (point, normal, uv, material; :568-574,:616-631,:706-728)
+template <typename R, bool CpuSem>
+__device__ __forceinline__ void make_surface(const SceneDev &S, const Ray<R> &r, const Hit<R> &h, Surface<R> &sf) {
+    sf.p = r.o + r.d * h.t;
+    const real4<R> *sh = reinterpret_cast<const real4<R> *>(S.shade) + 3 * h.prim;
+    if (h.prim < S.n_rect) {
+        const real4<R> *q = reinterpret_cast<const real4<R> *>(S.rect) + 4 * h.prim;
+        real4<R> r0 = ldg4(q), r1 = ldg4(q + 1);
+        sf.n = xyz<R>(r1);
+        sf.u = h.a / r0.w; sf.v = h.b / r1.w;
+    } else if (h.prim < S.n_rect + S.n_sphere) {
+        const real4<R> *q = reinterpret_cast<const real4<R> *>(S.sphere) + 2 * (h.prim - S.n_rect);
+        real4<R> s0 = ldg4(q);
+        sf.n = (sf.p - xyz<R>(s0)) / s0.w;
+        sf.u = R(0); sf.v = R(0);
+    } else {
+        real4<R> nn = ldg4(sh), uva = ldg4(sh + 1), uvb = ldg4(sh + 2);
+        V3<R> n = xyz<R>(nn);
+        R dp = dot(n, r.d);
+        bool flip = CpuSem ? !(dp < R(0)) : (dp > R(0));
+        sf.n = flip ? -n : n;
+        if (uvb.z != R(0)) {
+            R w = R(1) - h.a - h.b;
+            if (CpuSem) {      // u*uv1 + v*uv2 + w*uv0   (core/geometry.py:166-168)
+                sf.u = h.a * uva.z + h.b * uvb.x + w * uva.x;
+                sf.v = h.a * uva.w + h.b * uvb.y + w * uva.y;
+            } else {           // w*uv0 + u*uv1 + v*uv2   (cuda_path_tracer.py:722-724)
+                sf.u = w * uva.x + h.a * uva.z + h.b * uvb.x;
+                sf.v = w * uva.y + h.a * uva.w + h.b * uvb.y;
+            }
+        } else { sf.u = R(0); sf.v = R(0); }
+    }
+    int m = __ldg(S.prim_mat + h.prim);
+    const real4<R> *mq = reinterpret_cast<const real4<R> *>(S.mat) + 2 * m;
+    real4<R> m0 = ldg4(mq), m1 = ldg4(mq + 1);
+    sf.color = xyz<R>(m0); sf.diffuse = m0.w;
+    sf.specular = m1.x; sf.reflective = m1.y; sf.refractive = m1.z; sf.ior = m1.w;
+    sf.tex = __ldg(S.mat_tex + m);
+}
+
+// nearest-texel fetch with V flip: cuda_sample_texture (cuda_path_tracer.py:473-493) /
+// Texture.sample (core/material.py:13-21).  RGBX8 texel -> one 32-bit load.
+template <typename R, bool CpuSem>
+__device__ __forceinline__ V3<R> sample_texture(const SceneDev &S, int tex, R u, R v) {
+    int4 info = __ldg(S.tex_info + tex);       // offset, w, h
+    int w = info.y, h = info.z;
+    int iu, iv;
+    if (CpuSem) {
+        iu = (int)max_(R(0), min_(R(w - 1), u * R(w - 1)));
+        iv = (int)max_(R(0), min_(R(h - 1), (R(1) - v) * R(h - 1)));
+    } else {
+        u = max_(R(0), min_(R(1), u));
+        v = max_(R(0), min_(R(1), v));
+        iu = (int)(u * R(w - 1));
+        iv = (int)((R(1) - v) * R(h - 1));
+        iu = max(0, min(w - 1, iu));
+        iv = max(0, min(h - 1, iv));
+    }
+    uint32_t px = __ldg(S.texels + (size_t)info.x + (size_t)iv * w + iu);
+    return V3<R>{R(px & 255u) / R(255), R((px >> 8) & 255u) / R(255), R((px >> 16) & 255u) / R(255)};
+}
+
+template <typename R, bool CpuSem>
+__device__ __forceinline__ V3<R> base_color(const SceneDev &S, const Surface<R> &sf) {
+    if (sf.tex >= 0 && sf.tex < S.n_tex) return sample_texture<R, CpuSem>(S, sf.tex, sf.u, sf.v);
+    return sf.color;
+}
+
+// pinhole ray: cuda_get_ray (cuda_path_tracer.py:84-112) == Camera.get_ray + Ray() (core/camera.py:26-31)
+template <typename R>
+__device__ __forceinline__ Ray<R> camera_ray(const Cam<R> &c, R u, R v) {
+    Ray<R> r;
+    r.o = c.origin;
+    V3<R> d = {c.llc.x + u * c.hor.x + v * c.ver.x - c.origin.x,
+               c.llc.y + u * c.hor.y + v * c.ver.y - c.origin.y,
+               c.llc.z + u * c.hor.z + v * c.ver.z - c.origin.z};
+    R l = length(d);
+    if (l > R(0)) d = d / l;
+    r.d = d;
+    return r;
+}
+
+// Snell refraction: cuda_refract_path (cuda_path_tracer.py:115-131)
+template <typename R>
+__device__ __forceinline__ bool refract_nb(V3<R> in, V3<R> n, R eta, V3<R> &out) {
+    R cos_i = -(in.x * n.x + in.y * n.y + in.z * n.z);
+    R sin2_t = eta * eta * (R(1) - cos_i * cos_i);
+    if (sin2_t > R(1)) return false;
+    R cos_t = sqrt_(R(1) - sin2_t);
+    R f2 = eta * cos_i - cos_t;
+    out = {eta * in.x + f2 * n.x, eta * in.y + f2 * n.y, eta * in.z + f2 * n.z};
+    return true;
+}
+
+}  // namespace b2rt
