@@ -129,7 +129,8 @@ int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, 
                               int32_t max_depth, size_t *h_bytes);
 /*
  * Adds `spp_local` samples per pixel (global sample indices sample_offset .. sample_offset+spp_local-1)
- * to d_accum (real[4*H*W]: sum r, g, b, unused), in waves of spp_per_wave.
+ * to d_accum (real[4*H*W]: sum r, g, b, unused), in waves of spp_per_wave.  d_accum_sq (optional, same
+ * shape) receives the per-pixel sum of SQUARED per-sample radiance, for Monte-Carlo variance estimates.
  * rng_mode PCG: seed keys the streams.  rng_mode REFERENCE: seed is the reference's frame_count and
  * d_pixel_rng (int64[H*W], caller-zeroed before sample 0... see DESIGN.md) carries the per-pixel state.
  * d_counters (optional) uint64[8], accumulated: [0] paths, [1] closest-hit rays, [2] shadow rays,
@@ -137,7 +138,7 @@ int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, 
  */
 int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
                      int32_t spp_local, int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth,
-                     int32_t rng_mode, uint64_t seed, void *d_accum, int64_t *d_pixel_rng,
+                     int32_t rng_mode, uint64_t seed, void *d_accum, void *d_accum_sq, int64_t *d_pixel_rng,
                      void *d_workspace, size_t workspace_bytes, uint64_t *d_counters, void *stream);
 /* mean = accum / spp_total, optional ACES tonemap (cuda_tonemap, :74-81), quantise (:56-58), and write the
  * FLIPPED image (row 0 = top, replaces np.flip, :807) into d_u8 uint8[3*H*W]. */

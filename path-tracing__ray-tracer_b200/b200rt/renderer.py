@@ -122,7 +122,7 @@ class B200PathTracer(_B200Base):
                 "lbvh_acceleration", "wavefront", "multi_gpu"]
 
     # -- pieces usable on their own (bench.py times accumulate() with inputs resident in HBM) --------
-    def prepare(self, scene, camera, settings) -> dict:
+    def prepare(self, scene, camera, settings, want_sumsq: bool = False) -> dict:
         ds = self._upload(scene, camera)
         W, H, spp, depth = settings.width, settings.height, settings.samples_per_pixel, settings.max_depth
         rank, world = dist.rank_world()
@@ -138,6 +138,7 @@ class B200PathTracer(_B200Base):
         real = _torch_real(self.precision)
         st = dict(ds=ds, W=W, H=H, spp=spp, depth=depth, spp_local=spp_local, offset=offset, wave=wave,
                   accum=torch.zeros(W * H * 4, dtype=real, device=self.device),
+                  accum_sq=torch.zeros(W * H * 4, dtype=real, device=self.device) if want_sumsq else None,
                   counters=torch.zeros(8, dtype=torch.int64, device=self.device),
                   pixel_rng=torch.zeros(W * H, dtype=torch.int64, device=self.device),
                   u8=torch.empty(W * H * 3, dtype=torch.uint8, device=self.device),
@@ -149,7 +150,8 @@ class B200PathTracer(_B200Base):
         seed = self.frame_count if self.rng_mode == _lib.RNG_REFERENCE else self.seed + 0x9E3779B97F4A7C15 * self.frame_count
         _lib.check(self.lib.b2rt_render_path(
             st["ds"].ref(), st["cam"], st["W"], st["H"], st["spp_local"], st["offset"], st["wave"], st["depth"],
-            self.rng_mode, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), st["accum"].data_ptr(), st["pixel_rng"].data_ptr(),
+            self.rng_mode, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), st["accum"].data_ptr(),
+            st["accum_sq"].data_ptr() if st["accum_sq"] is not None else None, st["pixel_rng"].data_ptr(),
             self._ws.data_ptr(), self._ws.numel(), st["counters"].data_ptr(), current_stream_ptr(self.device)),
             "b2rt_render_path")
 
@@ -159,15 +161,21 @@ class B200PathTracer(_B200Base):
                                          current_stream_ptr(self.device)), "b2rt_resolve")
         return st["u8"]
 
-    def render_accum(self, scene, camera, settings):
-        """float sums [H, W, 4] (device row order) + counters, without tone mapping (tests/analysis)."""
+    def render_accum(self, scene, camera, settings, want_sumsq: bool = False):
+        """float sums [H, W, 4] (device row order) + counters, without tone mapping (tests/analysis).
+        With ``want_sumsq`` a third array holds the per-pixel sums of squared per-sample radiance."""
         with torch.cuda.device(self.device):
-            st = self.prepare(scene, camera, settings)
+            st = self.prepare(scene, camera, settings, want_sumsq)
             self.accumulate(st)
             dist.reduce_to_root(st["accum"])
+            if want_sumsq:
+                dist.reduce_to_root(st["accum_sq"])
             torch.cuda.synchronize(self.device)
             self.frame_count += 1
-            return st["accum"].reshape(st["H"], st["W"], 4).cpu().numpy(), st["counters"].cpu().numpy()
+            out = (st["accum"].reshape(st["H"], st["W"], 4).cpu().numpy(), st["counters"].cpu().numpy())
+            if want_sumsq:
+                out += (st["accum_sq"].reshape(st["H"], st["W"], 4).cpu().numpy(),)
+            return out
 
     def render(self, scene, camera, settings):
         t0 = time.perf_counter()

@@ -147,7 +147,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             buf ^= 1;
         }
         prof_begin(kAccumulate, st);
-        accumulate_kernel<R><<<g_simple, T, 0, st>>>(npix, k, Q.L, (real4<R> *)a.accum);
+        accumulate_kernel<R><<<g_simple, T, 0, st>>>(npix, k, Q.L, (real4<R> *)a.accum, (real4<R> *)a.accum_sq);
         prof_end(st);
         ++launches;
         if (a.counters) {

@@ -20,7 +20,7 @@ struct PathArgs {
     int width, height, spp_local, spp_per_wave, max_depth, rng_mode;
     long long sample_offset;
     unsigned long long seed;
-    void *accum;
+    void *accum, *accum_sq;
     long long *pixel_rng;
     void *workspace;
     size_t workspace_bytes;

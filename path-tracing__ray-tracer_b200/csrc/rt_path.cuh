@@ -296,17 +296,24 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
 // per-pixel radiance accumulation: accum[pix] += sum_s L[s][pix], samples in index order (:43-45)
 template <typename R>
 __global__ void __launch_bounds__(256)
-accumulate_kernel(int npix, int spp_wave, const real4<R> *__restrict__ L, real4<R> *__restrict__ accum) {
+accumulate_kernel(int npix, int spp_wave, const real4<R> *__restrict__ L, real4<R> *__restrict__ accum,
+                  real4<R> *__restrict__ accum_sq) {
     for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
         // wave-local partial sum first: the float32 running sum then sees one add per wave, not per sample
-        R sx = R(0), sy = R(0), sz = R(0);
+        R sx = R(0), sy = R(0), sz = R(0), qx = R(0), qy = R(0), qz = R(0);
         for (int s = 0; s < spp_wave; ++s) {
             real4<R> l = L[(size_t)s * npix + pix];
             sx += l.x; sy += l.y; sz += l.z;
+            qx += l.x * l.x; qy += l.y * l.y; qz += l.z * l.z;
         }
         real4<R> a = accum[pix];
         a.x += sx; a.y += sy; a.z += sz;
         accum[pix] = a;
+        if (accum_sq) {
+            real4<R> q = accum_sq[pix];
+            q.x += qx; q.y += qy; q.z += qz;
+            accum_sq[pix] = q;
+        }
     }
 }
 

@@ -192,40 +192,47 @@ def test_path_reference_rng_f64_replays_reference(scene, cam169, golden_dir, fc)
 
 def test_path_f32_statistics_vs_oracle(scene, cam169):
     """(c) float32 production kernels with the counter-based RNG against the oracle (reference RNG,
-    float64): normalised squared error ~ 1 and >= 99.5 % of values inside 3 sigma.  Pixels that miss
-    the box have zero variance and must equal the 0.1 sky exactly (8-bit value 32)."""
+    float64) at matched spp.  Stated tolerance (the reference's own noise floor measured
+    oracle-vs-oracle: statistic 1.06, 99.79 % inside): with sigma^2 = var_ref/n + var_gpu/n per pixel
+    and channel, mean(delta^2 / sigma^2) in [0.8, 1.25] and >= 99.5 % of values inside 3 sigma.
+    Pixels that miss the box must equal the 0.1 sky (8-bit value 32)."""
     W, H, D = 160, 90, 8
-    n_ref, n_gpu = 1024, 1024
-    ref = O.nb_path_trace(O.nb_pack(scene, cam169), W, H, n_ref, D)
-    mean_ref = ref["sum"] / n_ref
-    var_ref = np.maximum(ref["sumsq"] / n_ref - mean_ref ** 2, 0) * n_ref / (n_ref - 1)
+    n = 1024
+    ref = O.nb_path_trace(O.nb_pack(scene, cam169), W, H, n, D)
+    mean_ref = ref["sum"] / n
+    var_ref = np.maximum(ref["sumsq"] / n - mean_ref ** 2, 0) * n / (n - 1)
     r = renderer.B200PathTracer(precision="f32", rng="pcg", seed=7)
-    acc, cnt = r.render_accum(scene, cam169, RenderSettings(W, H, n_gpu, D))
-    mean_gpu = acc[..., :3].astype(np.float64) / n_gpu
-    # the GPU variance is estimated from a second, independent render's difference
-    r2 = renderer.B200PathTracer(precision="f32", rng="pcg", seed=8)
-    acc2, _ = r2.render_accum(scene, cam169, RenderSettings(W, H, n_gpu, D))
-    mean_gpu2 = acc2[..., :3].astype(np.float64) / n_gpu
+    acc, cnt, sq = r.render_accum(scene, cam169, RenderSettings(W, H, n, D), want_sumsq=True)
+    mean_gpu = acc[..., :3].astype(np.float64) / n
+    var_gpu = np.maximum(sq[..., :3].astype(np.float64) / n - mean_gpu ** 2, 0) * n / (n - 1)
     from scipy.ndimage import minimum_filter
-    lit = var_ref > 1e-12                    # zero-variance pixels: sky, and mirror-to-sky chains
     ids, _ = O.nb_primary_hits(O.nb_pack(scene, cam169, with_textures=False), W, H)
     sky = minimum_filter((ids < 0).astype(np.uint8), size=3).astype(bool)             # whole footprint misses
     assert sky.sum() > 1000
     assert np.abs(mean_gpu[sky] - 0.1).max() < 5e-6
     assert np.abs(mean_ref[sky] - 0.1).max() < 1e-12
-    sigma2 = 2 * var_ref / n_ref                      # both estimators have ~ the same variance
+    lit = (var_ref > 1e-12) & (var_gpu > 1e-12)
+    sigma2 = (var_ref + var_gpu) / n
     z2 = (mean_gpu - mean_ref) ** 2 / np.where(lit, sigma2, 1)
     stat = z2[lit].mean()
     inside = (np.abs(mean_gpu - mean_ref)[lit] <= 3 * np.sqrt(sigma2[lit])).mean()
-    # self-consistency of the same statistic between two GPU renders
-    z2_self = (mean_gpu - mean_gpu2) ** 2 / np.where(lit, sigma2, 1)
-    assert 0.5 < z2_self[lit].mean() < 1.5, z2_self[lit].mean()
-    assert 0.6 < stat < 1.5, stat
-    assert inside >= 0.99, inside
+    assert 0.8 < stat < 1.25, stat
+    assert inside >= 0.995, inside
+    # zero-variance pixels of either estimator (sky, mirror-to-sky chains) agree closely
+    flat = ~(var_ref > 1e-12).any(axis=2) & ~(var_gpu > 1e-12).any(axis=2)
+    assert np.abs(mean_gpu[flat] - mean_ref[flat]).max() < 1e-5
+    # relative RMSE of the means is at the reference's own noise floor (0.08 absolute at 1024 spp)
+    rmse = np.sqrt(((mean_gpu - mean_ref) ** 2).mean())
+    assert rmse < 0.12, rmse
+    # global energy: the image mean is a low-variance statistic
+    assert abs(mean_gpu.mean() - mean_ref.mean()) / mean_ref.mean() < 0.02
     # ray statistics match the reference algorithm's (SURVEY 3.1: 2.31 segments, 3.85 rays per path)
     rays_per_path = cnt[1] / cnt[0]
-    ref_rpp = ref["counters"]["closest_rays"] / (W * H * n_ref)
+    ref_rpp = ref["counters"]["closest_rays"] / (W * H * n)
     assert abs(rays_per_path - ref_rpp) / ref_rpp < 0.02
+    unshadowed = cnt[3] / cnt[0]
+    ref_un = ref["counters"]["nee_unshadowed"] / (W * H * n)
+    assert abs(unshadowed - ref_un) / ref_un < 0.05
 
 
 def test_path_sample_split_is_exact(scene, cam169):
