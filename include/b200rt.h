@@ -75,6 +75,11 @@ typedef struct b2rt_scene {
     const void *d_bvh_top;       /* float4[4*n_top]: breadth-first copy of the top levels (staged in smem)*/
     int32_t n_bvh_top;
     int32_t bvh_root;            /* child reference of the root: >= 0 node, < 0 means ~prim               */
+    int32_t scan_incoherent;     /* 1: rays after the first bounce and shadow rays scan ALL primitives in
+                                    packed order (every lane of a warp tests the same primitive: no SIMT
+                                    divergence) instead of walking the LBVH — faster when n_prims is a few
+                                    dozen (profiles/r1a: LBVH walk 3.8-11 of 32 lanes active)             */
+    int32_t reserved_;
 } b2rt_scene;
 
 const char *b2rt_last_error(void);

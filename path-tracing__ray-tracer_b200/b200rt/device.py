@@ -11,6 +11,7 @@ from . import _lib
 from .packer import PackedScene
 
 TOP_NODES_DEFAULT = 512      # BVH nodes staged in shared memory per CTA (64 B each -> 32 KB)
+SCAN_MAX_PRIMS = 64          # scenes this small scan all primitives for incoherent rays (b2rt_scene.scan_incoherent)
 
 
 def require_cuda(device: Optional[torch.device] = None) -> torch.device:
@@ -37,7 +38,8 @@ class DeviceScene:
     """Uploads a ``PackedScene`` in the requested precision and builds its LBVH on the device."""
 
     def __init__(self, packed: PackedScene, precision: int = _lib.P_F32, device=None,
-                 top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None):
+                 top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
+                 scan_max_prims: int = SCAN_MAX_PRIMS):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.packed = packed
@@ -91,6 +93,7 @@ class DeviceScene:
         s.d_texels, s.d_tex_info, s.d_lights = self.texels.data_ptr(), self.tex_info.data_ptr(), self.lights.data_ptr()
         s.d_bvh_nodes, s.d_bvh_top = self.nodes.data_ptr(), self.top.data_ptr()
         s.n_bvh_top, s.bvh_root = self.n_top, self.root
+        s.scan_incoherent = 1 if 0 < packed.n_prims <= scan_max_prims else 0
         self.struct = s
 
     def ref(self):

@@ -135,7 +135,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         int buf = 0;
         for (int b = 0; b < a.max_depth; ++b) {
             prof_begin(kExtend, st);
-            extend_kernel<R><<<g_extend, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.ray_count + b);
+            extend_kernel<R><<<g_extend, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.ray_count + b,
+                                                        (b > 0 && S.scan_incoherent) ? 1 : 0);
             prof_end(st);
             prof_begin(kShade, st);
             shade_kernel<R, Rng><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth);

@@ -112,15 +112,16 @@ static __global__ void init_pixel_rng_kernel(int W, int H, long long frame_count
 template <typename R>
 __global__ void __launch_bounds__(256)
 extend_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__restrict__ rd,
-              real4<R> *__restrict__ hit, const int *__restrict__ count) {
+              real4<R> *__restrict__ hit, const int *__restrict__ count, int scan) {
     extern __shared__ float4 s_top[];
-    stage_top(S, s_top);
+    if (!scan) stage_top(S, s_top);
     int n = *count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         real4<R> a = ro[i], b = rd[i];
         Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
         Hit<R> h;
-        traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
+        if (scan) scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
+        else traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
         hit[i] = Real4<R>::make(h.t, pack_int<R>((int64_t)h.prim), h.a, h.b);
     }
 }
@@ -271,7 +272,7 @@ template <typename R>
 __global__ void __launch_bounds__(256)
 shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
     extern __shared__ float4 s_top[];
-    stage_top(S, s_top);
+    if (!S.scan_incoherent) stage_top(S, s_top);
     int n = Q.shadow_count[bounce];
     int n_round = (n + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -280,7 +281,8 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
             real4<R> a = Q.so[i], b = Q.sd[i];
             Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
             Hit<R> h;
-            lit = !traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);   // :275-277 t_max = 1e6
+            lit = S.scan_incoherent ? !scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h)
+                                    : !traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);   // :275-277
             if (lit) {
                 int slot = (int)unpack_u<R>(a.w);
                 real4<R> c = Q.sc[i], l = Q.L[slot];

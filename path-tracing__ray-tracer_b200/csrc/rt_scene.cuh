@@ -25,6 +25,7 @@ struct SceneDev {
     const int4 *tex_info;
     const float4 *nodes, *top;
     int n_top, root;
+    int scan_incoherent;
 };
 
 inline SceneDev make_scene_dev(const b2rt_scene *s) {
@@ -40,6 +41,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.nodes = reinterpret_cast<const float4 *>(s->d_bvh_nodes);
     d.top = reinterpret_cast<const float4 *>(s->d_bvh_top);
     d.n_top = s->n_bvh_top; d.root = s->bvh_root;
+    d.scan_incoherent = s->scan_incoherent;
     return d;
 }
 

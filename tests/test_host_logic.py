@@ -1,0 +1,205 @@
+"""CPU tests of the host side: API mirror, packer, C-ABI surface, sample split, gloo reduce."""
+import ctypes
+import os
+import random
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plugin_registry_contract():
+    from b200rt import plugin
+    class R(plugin.BaseRenderer):
+        def __init__(self, tag="x"):
+            super().__init__("dummy"); self.tag = tag
+        def render(self, scene, camera, settings): return None
+        def get_capabilities(self): return ["a", "b"]
+    plugin.RendererFactory.register("dummy", R)
+    r = plugin.RendererFactory.create("dummy", tag="y")
+    assert r.get_name() == "dummy" and r.tag == "y" and r.supports("a") and not r.supports("z")
+    assert "dummy" in plugin.RendererFactory.list_available()
+    with pytest.raises(ValueError):
+        plugin.RendererFactory.create("nope")
+
+
+def test_scene_api_semantics():
+    from b200rt.scene_api import AABB, HitRecord, Material, Plane, Ray, Sphere, Triangle, Vec3
+    r = Ray(Vec3(0, 0, 5), Vec3(0, 0, -2))
+    assert r.direction.z == -1.0
+    rec = HitRecord()
+    s = Sphere(Vec3(0, 0, 0), 1.0, Material())
+    assert s.hit(r, 1e-3, float("inf"), rec) and rec.t == 4.0 and rec.normal.z == 1.0
+    p = Plane(Vec3(-1, -1, 0), Vec3(0, 0, 1), Vec3(2, 0, 0), Vec3(0, 2, 0), 2, 2, Material())
+    assert p.hit(r, 1e-3, 5.0, rec) and rec.t == 5.0          # closed range on t_max
+    assert (rec.u, rec.v) == (0.5, 0.5)
+    t = Triangle(Vec3(-1, -1, 0), Vec3(1, -1, 0), Vec3(0, 1, 0), np.array([0, 0]), np.array([1, 0]), np.array([0, 1]), Material())
+    assert t.hit(r, 1e-3, float("inf"), rec) and rec.normal.z == 1.0
+    assert not t.hit(r, 1e-3, 5.0, rec)                       # strict upper bound
+    with pytest.raises(ZeroDivisionError):
+        AABB(Vec3(-1, -1, -1), Vec3(1, 1, 1)).hit(r, 0, 10)
+    ok, d = Vec3(0, -1, 0).refract(Vec3(0, 1, 0), 1 / 1.5)
+    assert ok and abs(d.y + 1) < 1e-12
+
+
+def test_cornell_builder_matches_reference_when_present(cornell):
+    """Bit-for-bit agreement with the reference's CustomSceneBuilder (container only)."""
+    from oracle import ref_harness as RH
+    if not RH.available():
+        pytest.skip("reference not mounted")
+    ref_scene, ref_cam = RH.build_reference_scene(0, 16 / 9)
+    scene, b = cornell
+    def sig(o):
+        n = type(o).__name__
+        if n == "Plane":
+            return (n, *o.anchor.__dict__.values()) if hasattr(o.anchor, "__dict__") else \
+                (n, o.anchor.x, o.anchor.y, o.anchor.z, o.normal.x, o.normal.y, o.normal.z, o.u_unit.x, o.v_unit.z, o.u_len)
+        if n == "Sphere":
+            return (n, o.center.x, o.center.y, o.center.z, o.radius, o.material.refractive, o.material.ior)
+        return (n, o.v0.x, o.v0.y, o.v0.z, o.v1.x, o.v1.y, o.v1.z, o.v2.x, o.v2.y, o.v2.z, o.normal.x, o.normal.y,
+                o.normal.z, tuple(o.uv0), tuple(o.uv1), tuple(o.uv2), o.material.texture.path)
+    def sig2(o):
+        n = type(o).__name__
+        if n == "Plane":
+            return (n, o.anchor.x, o.anchor.y, o.anchor.z, o.normal.x, o.normal.y, o.normal.z, o.u_unit.x, o.v_unit.z, o.u_len)
+        return sig(o)
+    assert [sig2(o) for o in scene.objects] == [sig2(o) for o in ref_scene.objects]
+    assert [(l.x, l.y, l.z) for l in scene.lights] == [(l.x, l.y, l.z) for l in ref_scene.lights]
+    cam = b.create_camera(16 / 9)
+    for f in ("origin", "lower_left_corner", "horizontal", "vertical"):
+        assert getattr(cam, f).x == getattr(ref_cam, f).x and getattr(cam, f).z == getattr(ref_cam, f).z
+
+
+def test_packer_layout(cornell, golden_dir):
+    """SoA streams vs the reference's AoS block (golden): same values, derived fields as Numba rounds them."""
+    from b200rt import packer
+    scene, b = cornell
+    p = packer.pack_scene(scene, "numba")
+    sd = np.load(f"{golden_dir}/packed_scene_seed0.npz")["scene"]
+    nP = int(sd[0]); pl = sd[1:1 + 20 * nP].reshape(nP, 20); off = 1 + 20 * nP
+    nS = int(sd[off]); sp = sd[off + 1: off + 1 + 12 * nS].reshape(nS, 12); off += 1 + 12 * nS
+    nT = int(sd[off]); tr = sd[off + 1:].reshape(nT, 26)
+    assert (p.n_rect, p.n_sphere, p.n_tri) == (nP, nS, nT) == (5, 3, 26)
+    R = p.rect.reshape(-1, 4, 4)
+    assert np.array_equal(R[:, 0, :3], pl[:, 0:3]) and np.array_equal(R[:, 1, :3], pl[:, 3:6])
+    assert np.array_equal(R[:, 0, 3], pl[:, 12]) and np.array_equal(R[:, 1, 3], pl[:, 13])
+    un = np.sqrt((pl[:, 6:9] ** 2).sum(1, dtype=np.float32), dtype=np.float32)
+    assert np.array_equal(R[:, 2, :3], (pl[:, 6:9] / un[:, None]).astype(np.float64))
+    S = p.sphere.reshape(-1, 2, 4)
+    assert np.array_equal(S[:, 0], sp[:, 0:4]) and np.array_equal(S[:, 1, 0], (sp[:, 3] * sp[:, 3]))
+    T = p.tri.reshape(-1, 3, 4)
+    assert np.array_equal(T[:, 0, :3], tr[:, 0:3])
+    assert np.array_equal(T[:, 1, :3], (tr[:, 3:6] - tr[:, 0:3]).astype(np.float64))
+    assert np.array_equal(T[:, 2, :3], (tr[:, 6:9] - tr[:, 0:3]).astype(np.float64))
+    SH = p.shade.reshape(-1, 3, 4)[nP + nS:]
+    assert np.array_equal(SH[:, 0, :3], tr[:, 9:12]) and np.array_equal(SH[:, 1], tr[:, 20:24])
+    # materials: planes/triangles never refractive, only triangles textured (numba semantics)
+    M = p.mat.reshape(-1, 2, 4)
+    tri_m = p.prim_mat[nP + nS:]
+    assert np.array_equal(M[tri_m, 0, :3], tr[:, 12:15]) and np.array_equal(p.mat_tex[tri_m], tr[:, 19].astype(np.int32))
+    assert (M[p.prim_mat[:nP], 1, 2] == 0).all() and (p.mat_tex[p.prim_mat[:nP + nS]] == -1).all()
+    assert np.array_equal(M[p.prim_mat[nP:nP + nS], 1, 2:4], sp[:, 10:12])
+    # textures: RGBX8, ids by sorted path
+    texels, info, ids = packer.pack_textures(scene)
+    assert info[:, 1:3].tolist() == [[1318, 1319], [1317, 1316], [2978, 2393], [1269, 1268], [1315, 1314], [1296, 1296], [1320, 1320]]
+    assert texels.size == 52070958 // 3 and (texels >> 24 == 255).all()
+    t0 = scene.objects[[type(o).__name__ for o in scene.objects].index("Triangle")].material.texture
+    k = ids[t0.path]
+    px = texels[info[k, 0] + 5 * info[k, 1] + 7]
+    assert (px & 255, (px >> 8) & 255, (px >> 16) & 255) == tuple(int(v) for v in t0.pixels[5, 7])
+    # cpu semantics keep un-rounded doubles and full materials
+    pc = packer.pack_scene(scene, "cpu")
+    assert pc.semantics == 1 and (pc.sphere.reshape(-1, 2, 4)[:, 1, 0] == 9.0).all()
+    assert pc.order[:, 0].tolist() == p.order[:, 0].tolist()
+
+
+def test_triangle_mesh_side_door():
+    from b200rt import packer
+    from b200rt.scene_api import Material, Scene, Triangle, Vec3
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    f = np.array([[0, 1, 2], [0, 2, 3]])
+    a, b_ = Scene(), Scene()
+    m = Material(Vec3(0.5, 0.6, 0.7), diffuse=0.8)
+    a.objects.append(packer.TriangleMesh(v, f, m))
+    for tri in f:
+        b_.objects.append(Triangle(*(Vec3(*v[i]) for i in tri), None, None, None, m))
+    pa, pb = packer.pack_scene(a, "numba"), packer.pack_scene(b_, "numba")
+    assert np.array_equal(pa.tri, pb.tri) and np.array_equal(pa.shade, pb.shade)
+    assert pa.order.tolist() == [[0, 0], [0, 1]]
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libb200rt.so loads (no GPU needed) and exports exactly what include/b200rt.h declares."""
+    from b200rt import _lib, build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    hdr = open(os.path.join(ROOT, "include", "b200rt.h")).read()
+    declared = set(re.findall(r"\b(b2rt_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert ctypes.sizeof(_lib.SceneStruct) == 8 * 4 + 12 * 8 + 2 * 4 + 0 or ctypes.sizeof(_lib.SceneStruct) % 8 == 0
+    lib.b2rt_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.b2rt_last_error(), bytes)
+    nbytes = ctypes.c_size_t(0)
+    assert lib.b2rt_path_workspace_bytes(0, 1920, 1080, 8, 8, ctypes.byref(nbytes)) == 0
+    assert nbytes.value >= 1920 * 1080 * 8 * 176
+    assert lib.b2rt_path_workspace_bytes(0, 0, 0, 0, 0, ctypes.byref(nbytes)) != 0       # error path, no GPU call
+
+
+def test_renderer_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from b200rt import renderer
+    from b200rt.plugin import RendererFactory
+    assert {"b200_path_tracer", "b200_texture_raytracer", "b200_raytracer"} <= set(RendererFactory.list_available())
+    with pytest.raises(RuntimeError):
+        RendererFactory.create("b200_path_tracer")
+
+
+def test_split_samples_is_exhaustive_and_contiguous():
+    from b200rt.dist import split_samples
+    for spp in (1, 7, 8, 1024, 4096):
+        for world in (1, 2, 3, 4, 8):
+            parts = [split_samples(spp, r, world) for r in range(world)]
+            assert sum(p[0] for p in parts) == spp
+            off = 0
+            for n, o in parts:
+                assert o == off
+                off += n
+            assert max(p[0] for p in parts) - min(p[0] for p in parts) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as td
+from b200rt import dist
+td.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.rank_world()
+n, off = dist.split_samples(9, rank, world)
+buf = torch.full((16,), float(n), dtype=torch.float32) + off
+dist.reduce_to_root(buf)
+if rank == 0:
+    assert torch.allclose(buf, torch.full((16,), 9.0 + 5.0)), buf
+    print("root ok")
+td.destroy_process_group()
+"""
+
+
+def test_gloo_world2_reduce(tmp_path):
+    """N > 1 host path on CPU: two processes, spp split + one SUM reduce onto rank 0."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + random.randint(0, 400))
+    pkg = os.path.join(ROOT, "path-tracing__ray-tracer_b200")
+    procs = [subprocess.Popen([sys.executable, str(script), pkg, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "root ok" in outs[0]
