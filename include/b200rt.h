@@ -38,6 +38,9 @@ extern "C" {
 #define B2RT_SEM_NUMBA 0 /* cuda_path_tracer.py / cuda_texture_renderer.py: strict t range, `dot > 0` flips   */
 #define B2RT_SEM_CPU   1 /* core/geometry.py via cpu_renderer.py: Plane accepts t == t_max, `dot >= 0` flips */
 
+/* flags for b2rt_render_path */
+#define B2RT_PATH_UNFUSED 1
+
 /* rng modes for b2rt_render_path */
 #define B2RT_RNG_PCG       0 /* counter-based: stream keyed by (pixel, global sample index, seed)        */
 #define B2RT_RNG_REFERENCE 1 /* the reference's int64 xorshift, per-pixel sequential (cuda_path_tracer.py:28,61-71) */
@@ -138,12 +141,15 @@ int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, 
  * shape) receives the per-pixel sum of SQUARED per-sample radiance, for Monte-Carlo variance estimates.
  * rng_mode PCG: seed keys the streams.  rng_mode REFERENCE: seed is the reference's frame_count and
  * d_pixel_rng (int64[H*W], caller-zeroed before sample 0... see DESIGN.md) carries the per-pixel state.
+ * flags: B2RT_PATH_UNFUSED runs extend and shade as separate kernels through the hit stream (the default
+ * fuses them: closest hit and shading in one kernel per bounce).
  * d_counters (optional) uint64[8], accumulated: [0] paths, [1] closest-hit rays, [2] shadow rays,
  * [3] unshadowed light samples, [4] kernel launches made by this call.
  */
 int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
                      int32_t spp_local, int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth,
-                     int32_t rng_mode, uint64_t seed, void *d_accum, void *d_accum_sq, int64_t *d_pixel_rng,
+                     int32_t rng_mode, uint64_t seed, int32_t flags, void *d_accum, void *d_accum_sq,
+                     int64_t *d_pixel_rng,
                      void *d_workspace, size_t workspace_bytes, uint64_t *d_counters, void *stream);
 /* mean = accum / spp_total, optional ACES tonemap (cuda_tonemap, :74-81), quantise (:56-58), and write the
  * FLIPPED image (row 0 = top, replaces np.flip, :807) into d_u8 uint8[3*H*W]. */

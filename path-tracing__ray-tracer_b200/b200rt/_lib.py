@@ -65,7 +65,7 @@ def load():
     lib.b2rt_render_whitted_cpu.argtypes = [SP, C.POINTER(dbl), i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(dbl), vp, vp]
     lib.b2rt_render_whitted_texture.argtypes = [SP, C.POINTER(dbl), i32, i32, i32, i32, vp, vp, vp]
     lib.b2rt_path_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, C.POINTER(sz)]
-    lib.b2rt_render_path.argtypes = [SP, C.POINTER(dbl), i32, i32, i32, i64, i32, i32, i32, u64, vp, vp, vp, vp, sz, vp, vp]
+    lib.b2rt_render_path.argtypes = [SP, C.POINTER(dbl), i32, i32, i32, i64, i32, i32, i32, u64, i32, vp, vp, vp, vp, sz, vp, vp]
     lib.b2rt_resolve.argtypes = [i32, vp, i32, i32, dbl, i32, vp, vp]
     lib.b2rt_profile_enable.argtypes = [i32]
     lib.b2rt_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i64)]

@@ -107,8 +107,10 @@ class B200PathTracer(_B200Base):
     """
 
     def __init__(self, precision="f32", rng="pcg", seed: int = 0, spp_per_wave: Optional[int] = None,
-                 device=None, top_nodes: int = 512, wave_paths: int = 1 << 24, scan_max_prims: int = 64):
+                 device=None, top_nodes: int = 512, wave_paths: int = 1 << 24, scan_max_prims: int = 64,
+                 fused: bool = True):
         super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims)
+        self.flags = 0 if fused else 1
         self.rng_mode = _RNG[rng]
         self.seed = int(seed)
         self.spp_per_wave = spp_per_wave
@@ -151,7 +153,7 @@ class B200PathTracer(_B200Base):
         seed = self.frame_count if self.rng_mode == _lib.RNG_REFERENCE else self.seed + 0x9E3779B97F4A7C15 * self.frame_count
         _lib.check(self.lib.b2rt_render_path(
             st["ds"].ref(), st["cam"], st["W"], st["H"], st["spp_local"], st["offset"], st["wave"], st["depth"],
-            self.rng_mode, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), st["accum"].data_ptr(),
+            self.rng_mode, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), self.flags, st["accum"].data_ptr(),
             st["accum_sq"].data_ptr() if st["accum_sq"] is not None else None, st["pixel_rng"].data_ptr(),
             self._ws.data_ptr(), self._ws.numel(), st["counters"].data_ptr(), current_stream_ptr(self.device)),
             "b2rt_render_path")

@@ -160,6 +160,7 @@ int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, 
 
 int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height, int32_t spp_local,
                      int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth, int32_t rng_mode, uint64_t seed,
+                     int32_t flags,
                      void *d_accum, void *d_accum_sq, int64_t *d_pixel_rng, void *d_workspace, size_t workspace_bytes,
                      uint64_t *d_counters, void *stream) {
     if (int r = check_scene(scene)) return r;
@@ -168,7 +169,7 @@ int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width
         return fail_msg("render_path: wave larger than 2^31 paths");
     b2rt::PathArgs a;
     a.width = width; a.height = height; a.spp_local = spp_local; a.spp_per_wave = spp_per_wave;
-    a.max_depth = max_depth; a.rng_mode = rng_mode; a.sample_offset = sample_offset; a.seed = seed;
+    a.max_depth = max_depth; a.rng_mode = rng_mode; a.flags = flags; a.sample_offset = sample_offset; a.seed = seed;
     a.accum = d_accum; a.accum_sq = d_accum_sq; a.pixel_rng = (long long *)d_pixel_rng; a.workspace = d_workspace;
     a.workspace_bytes = workspace_bytes; a.counters = (unsigned long long *)d_counters;
     cudaError_t e = DISPATCH(scene->precision, Api<float>::render_path(scene, h_cam, a, S(stream)),

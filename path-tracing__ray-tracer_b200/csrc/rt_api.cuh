@@ -115,7 +115,10 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     static int g_extend = 0, g_shade = 0, g_shadow = 0, g_simple = 0;
     // persistent grids: resident CTAs per SM x SM count (a multiple of the 148 SMs)
     g_extend = persistent_grid((const void *)extend_kernel<R>, T, smem);
-    g_shade = persistent_grid((const void *)shade_kernel<R, Rng>, T, 0);
+    g_shade = persistent_grid((const void *)shade_kernel<R, Rng, 0>, T, 0);
+    const bool fused = !(a.flags & 1);
+    const int g_fuse_bvh = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem);
+    const int g_fuse_scan = persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, 0);
     g_shadow = persistent_grid((const void *)shadow_kernel<R>, T, smem);
     g_simple = persistent_grid((const void *)accumulate_kernel<R>, T, 0);
 
@@ -134,13 +137,21 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         ++launches;
         int buf = 0;
         for (int b = 0; b < a.max_depth; ++b) {
-            prof_begin(kExtend, st);
-            extend_kernel<R><<<g_extend, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.ray_count + b,
-                                                        (b > 0 && S.scan_incoherent) ? 1 : 0);
-            prof_end(st);
-            prof_begin(kShade, st);
-            shade_kernel<R, Rng><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth);
-            prof_end(st);
+            const bool scan = b > 0 && S.scan_incoherent;
+            if (fused) {
+                prof_begin(kShade, st);
+                if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, 0, st>>>(S, Q, buf, b, a.max_depth);
+                else shade_kernel<R, Rng, 1><<<g_fuse_bvh, T, smem, st>>>(S, Q, buf, b, a.max_depth);
+                prof_end(st);
+                launches -= 1;
+            } else {
+                prof_begin(kExtend, st);
+                extend_kernel<R><<<g_extend, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.ray_count + b, scan ? 1 : 0);
+                prof_end(st);
+                prof_begin(kShade, st);
+                shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth);
+                prof_end(st);
+            }
             prof_begin(kShadow, st);
             shadow_kernel<R><<<g_shadow, T, smem, st>>>(S, Q, b);
             prof_end(st);

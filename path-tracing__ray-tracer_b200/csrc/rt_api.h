@@ -17,7 +17,7 @@ void prof_begin(int cls, cudaStream_t st);
 void prof_end(cudaStream_t st);
 
 struct PathArgs {
-    int width, height, spp_local, spp_per_wave, max_depth, rng_mode;
+    int width, height, spp_local, spp_per_wave, max_depth, rng_mode, flags;
     long long sample_offset;
     unsigned long long seed;
     void *accum, *accum_sq;

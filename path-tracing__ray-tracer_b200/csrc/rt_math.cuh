@@ -25,6 +25,21 @@ __device__ __forceinline__ double4 ldg4(const double4 *p) {
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// streaming (evict-first) access for queue records that are touched exactly once per kernel, so they do
+// not push the small scene tables out of L1/L2
+__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ double4 ld_stream(const double4 *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 a = __ldcs(q), b = __ldcs(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(double4 *p, double4 v) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+    __stcs(q, make_double2(v.x, v.y));
+    __stcs(q + 1, make_double2(v.z, v.w));
+}
+
 template <typename R> struct V3 {
     R x, y, z;
 };
@@ -42,7 +57,6 @@ template <typename R> __device__ __forceinline__ R dot(V3<R> a, V3<R> b) { retur
 template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-__device__ __forceinline__ float rsqrt_(float x) { return sqrtf(x); }
 __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
@@ -53,11 +67,26 @@ __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float pow_(float a, float b) { return powf(a, b); }
 __device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
+// Division policy: the float64 parity instantiation divides exactly where the reference divides;
+// the float32 production instantiation multiplies by one correctly-rounded reciprocal (MUFU.RCP + fix-up)
+// instead of running the ~10-instruction IEEE division sequence per component.
+template <typename R> __device__ __forceinline__ R rcp_(R x) {
+    if constexpr (sizeof(R) == 4) return __frcp_rn(x);
+    else return R(1) / x;
+}
+template <typename R> __device__ __forceinline__ V3<R> div3(V3<R> a, R k) {
+    if constexpr (sizeof(R) == 4) { R r = __frcp_rn(k); return {a.x * r, a.y * r, a.z * r}; }
+    else return {a.x / k, a.y / k, a.z / k};
+}
+template <typename R> __device__ __forceinline__ R div_(R a, R b) {
+    if constexpr (sizeof(R) == 4) return a * __frcp_rn(b);
+    else return a / b;
+}
 template <typename R> __device__ __forceinline__ R length(V3<R> a) { return sqrt_(a.x * a.x + a.y * a.y + a.z * a.z); }
 // Vec3.normalize (core/math.py:49-53): divide by the length; the zero vector stays zero
 template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) {
     R l = length(a);
-    return l == R(0) ? V3<R>{R(0), R(0), R(0)} : a / l;
+    return l == R(0) ? V3<R>{R(0), R(0), R(0)} : div3(a, l);
 }
 template <typename R> __device__ __forceinline__ V3<R> cvt3(V3<double> a) { return {R(a.x), R(a.y), R(a.z)}; }
 

@@ -117,12 +117,12 @@ extend_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__res
     if (!scan) stage_top(S, s_top);
     int n = *count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        real4<R> a = ro[i], b = rd[i];
+        real4<R> a = ld_stream(ro + i), b = ld_stream(rd + i);
         Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
         Hit<R> h;
         if (scan) scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
         else traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
-        hit[i] = Real4<R>::make(h.t, pack_int<R>((int64_t)h.prim), h.a, h.b);
+        st_stream(hit + i, Real4<R>::make(h.t, pack_int<R>((int64_t)h.prim), h.a, h.b));
     }
 }
 
@@ -139,7 +139,7 @@ __device__ __forceinline__ V3<R> cos_hemisphere(V3<R> n, uint64_t &rng) {
     V3<R> t = abs_(n.z) > R(0.9) ? V3<R>{R(1), R(0), R(0)} : V3<R>{R(0), R(0), R(1)};
     V3<R> u = {t.y * n.z - t.z * n.y, t.z * n.x - t.x * n.z, t.x * n.y - t.y * n.x};
     R ul = length(u);
-    u = u / ul;
+    u = div3(u, ul);
     V3<R> v = {n.y * u.z - n.z * u.y, n.z * u.x - n.x * u.z, n.x * u.y - n.y * u.x};
     return {x * u.x + y * v.x + z * n.x, x * u.y + y * v.y + z * n.y, x * u.z + y * v.z + z * n.z};
 }
@@ -157,112 +157,141 @@ __device__ __forceinline__ int warp_append(int *counter, bool want) {
 }
 
 // ------------------------------------------------------------------------------------ shade
-// One loop iteration of cuda_trace_path (:229-469) for every queued path.
+template <typename R> struct Segment {       // what one loop iteration of cuda_trace_path produces
+    bool alive, want_shadow;
+    V3<R> new_o, new_d, thr, s_o, s_d, s_c;
+    uint64_t rng;
+};
+
+// One loop iteration of cuda_trace_path (:229-469) for one path: sky / texture / NEE shadow-ray
+// emission / Russian roulette / BSDF sampling.  thr and rng come in through g and are updated.
 template <typename R, typename Rng>
+__device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueues<R> &Q, const Ray<R> &r,
+                                              const Hit<R> &h, int slot, int bounce, int max_depth, Segment<R> &g) {
+    V3<R> &thr = g.thr, &new_o = g.new_o, &new_d = g.new_d, &s_o = g.s_o, &s_d = g.s_d, &s_c = g.s_c;
+    uint64_t &rng = g.rng;
+    bool &alive = g.alive, &want_shadow = g.want_shadow;
+    if (h.prim < 0) {                                                       // :234-239 sky
+        real4<R> l = Q.L[slot];
+        Q.L[slot] = Real4<R>::make(l.x + thr.x * R(0.1), l.y + thr.y * R(0.1), l.z + thr.z * R(0.1), l.w);
+    } else {
+        Surface<R> sf;
+        make_surface<R, false>(S, r, h, sf);
+        V3<R> mc = base_color<R, false>(S, sf);
+        V3<R> po = sf.p + sf.n * R(0.001);
+        if (S.n_lights > 0) {                                               // :265-304
+            R nl = R(S.n_lights);
+            int li = (int)(Rng::template random<R>(rng) * nl);
+            if (li >= S.n_lights) li = S.n_lights - 1;
+            rng = Rng::advance(rng);
+            V3<R> l = xyz<R>(ldg4(reinterpret_cast<const real4<R> *>(S.lights) + li)) - sf.p;
+            R dist = length(l);
+            if (dist > R(0.001)) l = div3(l, dist);
+            R pdf = R(1) / nl;
+            R ct = max_(R(0), l.x * sf.n.x + l.y * sf.n.y + l.z * sf.n.z);
+            R li_, lm;
+            if (sf.refractive > R(0.5)) { li_ = R(4.0); lm = R(0.6); }
+            else if (sf.reflective > R(0.7)) { li_ = R(2.5); lm = R(0.8); }
+            else { li_ = R(2.0); lm = R(1.0); }
+            s_c = {thr.x * (mc.x * sf.diffuse * ct * li_ * lm / pdf),
+                   thr.y * (mc.y * sf.diffuse * ct * li_ * lm / pdf),
+                   thr.z * (mc.z * sf.diffuse * ct * li_ * lm / pdf)};
+            // a shadow ray whose payload is exactly zero cannot change the image: not queued
+            want_shadow = (s_c.x != R(0)) || (s_c.y != R(0)) || (s_c.z != R(0));
+            s_o = po; s_d = l;
+        }
+        bool go = true;
+        if (bounce >= 3) {                                                  // :307-314
+            R p = max_(R(0.1), R(0.299) * thr.x + R(0.587) * thr.y + R(0.114) * thr.z);
+            if (Rng::template random<R>(rng) > p) go = false;
+            else { rng = Rng::advance(rng); thr = div3(thr, p); }
+        }
+        if (go) {
+            R choice = Rng::template random<R>(rng);                        // :317-318
+            rng = Rng::advance(rng);
+            R dn = r.d.x * sf.n.x + r.d.y * sf.n.y + r.d.z * sf.n.z;
+            V3<R> refl = {r.d.x - R(2) * dn * sf.n.x, r.d.y - R(2) * dn * sf.n.y, r.d.z - R(2) * dn * sf.n.z};
+            new_o = po;
+            if (sf.refractive > R(0.1)) {                                   // :320-428 glass
+                if (choice < R(0.6)) {
+                    R cos_i = max_(R(0), -dn);
+                    bool entering = cos_i > R(0);
+                    V3<R> on = entering ? sf.n : -sf.n;
+                    R eta = entering ? rcp_(sf.ior) : sf.ior;
+                    V3<R> rr;
+                    if (refract_nb<R>(r.d, on, eta, rr)) {
+                        if (entering) new_o = sf.p - sf.n * R(0.001);
+                        new_d = rr;
+                        thr = thr * (sf.refractive / R(0.6));
+                    } else { new_d = refl; thr = thr * R(0.9); }
+                } else if (choice < R(0.6) + R(0.25)) {
+                    new_d = refl;
+                    thr = {thr.x * (mc.x * R(0.9) / R(0.25)), thr.y * (mc.y * R(0.9) / R(0.25)),
+                           thr.z * (mc.z * R(0.9) / R(0.25))};
+                } else {
+                    new_d = cos_hemisphere<R, Rng>(sf.n, rng);
+                    thr = {thr.x * (mc.x * sf.diffuse * R(3.0) / R(0.15)), thr.y * (mc.y * sf.diffuse * R(3.0) / R(0.15)),
+                           thr.z * (mc.z * sf.diffuse * R(3.0) / R(0.15))};
+                }
+            } else if (sf.reflective > R(0.5)) {                            // :430-449 mirror
+                new_d = refl;
+                thr = {thr.x * (mc.x * sf.reflective), thr.y * (mc.y * sf.reflective), thr.z * (mc.z * sf.reflective)};
+            } else {                                                        // :451-466 diffuse
+                new_d = cos_hemisphere<R, Rng>(sf.n, rng);
+                thr = {thr.x * (mc.x * sf.diffuse), thr.y * (mc.y * sf.diffuse), thr.z * (mc.z * sf.diffuse)};
+            }
+            alive = !(max_(thr.x, max_(thr.y, thr.z)) < R(0.001))           // :468
+                    && (bounce + 1 < max_depth);                            // :229 loop bound
+        }
+    }
+}
+
+// MODE 0: wavefront "shade" stage reading the hit stream written by extend_kernel.
+// MODE 1/2: fused extend+shade — the closest hit is found in-register (1: LBVH walk, 2: warp-uniform scan
+// of all primitives) and shaded at once, so the FP32-issue-bound intersection work overlaps the
+// latency-bound shading loads in one kernel and the hit stream (32 B/segment) never touches HBM.
+template <typename R, typename Rng, int MODE>
 __global__ void __launch_bounds__(256)
 shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth) {
+    extern __shared__ float4 s_top[];
+    if (MODE == 1) stage_top(S, s_top);
     const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
     real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
     int n = Q.ray_count[bounce];
     int n_round = (n + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool valid = i < n;
-        bool alive = false, want_shadow = false;
-        V3<R> new_o, new_d, thr, s_o, s_d, s_c;
-        uint64_t rng = 0;
+        Segment<R> g;
+        g.alive = false; g.want_shadow = false; g.rng = 0;
         int slot = 0;
         if (valid) {
-            real4<R> a = ro[i], b = rd[i], c = th[i], hrec = Q.hit[i];
+            real4<R> a = ld_stream(ro + i), b = ld_stream(rd + i), c = ld_stream(th + i);
             Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
             slot = (int)unpack_u<R>(a.w);
-            rng = unpack_u<R>(b.w);
-            thr = xyz<R>(c);
-            Hit<R> h; h.t = hrec.x; h.prim = (int)(long long)real_as_int(hrec.y); h.a = hrec.z; h.b = hrec.w;
-            if (h.prim < 0) {                                                       // :234-239 sky
-                real4<R> l = Q.L[slot];
-                Q.L[slot] = Real4<R>::make(l.x + thr.x * R(0.1), l.y + thr.y * R(0.1), l.z + thr.z * R(0.1), l.w);
+            g.rng = unpack_u<R>(b.w);
+            g.thr = xyz<R>(c);
+            Hit<R> h;
+            if (MODE == 0) {
+                real4<R> hrec = ld_stream(Q.hit + i);
+                h.t = hrec.x; h.prim = (int)(long long)real_as_int(hrec.y); h.a = hrec.z; h.b = hrec.w;
+            } else if (MODE == 1) {
+                traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
             } else {
-                Surface<R> sf;
-                make_surface<R, false>(S, r, h, sf);
-                V3<R> mc = base_color<R, false>(S, sf);
-                V3<R> po = sf.p + sf.n * R(0.001);
-                if (S.n_lights > 0) {                                               // :265-304
-                    R nl = R(S.n_lights);
-                    int li = (int)(Rng::template random<R>(rng) * nl);
-                    if (li >= S.n_lights) li = S.n_lights - 1;
-                    rng = Rng::advance(rng);
-                    V3<R> l = xyz<R>(ldg4(reinterpret_cast<const real4<R> *>(S.lights) + li)) - sf.p;
-                    R dist = length(l);
-                    if (dist > R(0.001)) l = l / dist;
-                    R pdf = R(1) / nl;
-                    R ct = max_(R(0), l.x * sf.n.x + l.y * sf.n.y + l.z * sf.n.z);
-                    R li_, lm;
-                    if (sf.refractive > R(0.5)) { li_ = R(4.0); lm = R(0.6); }
-                    else if (sf.reflective > R(0.7)) { li_ = R(2.5); lm = R(0.8); }
-                    else { li_ = R(2.0); lm = R(1.0); }
-                    s_c = {thr.x * (mc.x * sf.diffuse * ct * li_ * lm / pdf),
-                           thr.y * (mc.y * sf.diffuse * ct * li_ * lm / pdf),
-                           thr.z * (mc.z * sf.diffuse * ct * li_ * lm / pdf)};
-                    // a shadow ray whose payload is exactly zero cannot change the image: not queued
-                    want_shadow = (s_c.x != R(0)) || (s_c.y != R(0)) || (s_c.z != R(0));
-                    s_o = po; s_d = l;
-                }
-                bool go = true;
-                if (bounce >= 3) {                                                  // :307-314
-                    R p = max_(R(0.1), R(0.299) * thr.x + R(0.587) * thr.y + R(0.114) * thr.z);
-                    if (Rng::template random<R>(rng) > p) go = false;
-                    else { rng = Rng::advance(rng); thr = thr / p; }
-                }
-                if (go) {
-                    R choice = Rng::template random<R>(rng);                        // :317-318
-                    rng = Rng::advance(rng);
-                    R dn = r.d.x * sf.n.x + r.d.y * sf.n.y + r.d.z * sf.n.z;
-                    V3<R> refl = {r.d.x - R(2) * dn * sf.n.x, r.d.y - R(2) * dn * sf.n.y, r.d.z - R(2) * dn * sf.n.z};
-                    new_o = po;
-                    if (sf.refractive > R(0.1)) {                                   // :320-428 glass
-                        if (choice < R(0.6)) {
-                            R cos_i = max_(R(0), -dn);
-                            bool entering = cos_i > R(0);
-                            V3<R> on = entering ? sf.n : -sf.n;
-                            R eta = entering ? R(1) / sf.ior : sf.ior;
-                            V3<R> rr;
-                            if (refract_nb<R>(r.d, on, eta, rr)) {
-                                if (entering) new_o = sf.p - sf.n * R(0.001);
-                                new_d = rr;
-                                thr = thr * (sf.refractive / R(0.6));
-                            } else { new_d = refl; thr = thr * R(0.9); }
-                        } else if (choice < R(0.6) + R(0.25)) {
-                            new_d = refl;
-                            thr = {thr.x * (mc.x * R(0.9) / R(0.25)), thr.y * (mc.y * R(0.9) / R(0.25)),
-                                   thr.z * (mc.z * R(0.9) / R(0.25))};
-                        } else {
-                            new_d = cos_hemisphere<R, Rng>(sf.n, rng);
-                            thr = {thr.x * (mc.x * sf.diffuse * R(3.0) / R(0.15)), thr.y * (mc.y * sf.diffuse * R(3.0) / R(0.15)),
-                                   thr.z * (mc.z * sf.diffuse * R(3.0) / R(0.15))};
-                        }
-                    } else if (sf.reflective > R(0.5)) {                            // :430-449 mirror
-                        new_d = refl;
-                        thr = {thr.x * (mc.x * sf.reflective), thr.y * (mc.y * sf.reflective), thr.z * (mc.z * sf.reflective)};
-                    } else {                                                        // :451-466 diffuse
-                        new_d = cos_hemisphere<R, Rng>(sf.n, rng);
-                        thr = {thr.x * (mc.x * sf.diffuse), thr.y * (mc.y * sf.diffuse), thr.z * (mc.z * sf.diffuse)};
-                    }
-                    alive = !(max_(thr.x, max_(thr.y, thr.z)) < R(0.001))           // :468
-                            && (bounce + 1 < max_depth);                            // :229 loop bound
-                }
+                scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
             }
+            shade_segment<R, Rng>(S, Q, r, h, slot, bounce, max_depth, g);
         }
-        int si = warp_append(Q.shadow_count + bounce, want_shadow);
-        if (want_shadow) {
-            Q.so[si] = Real4<R>::make(s_o.x, s_o.y, s_o.z, pack_int<R>((int64_t)slot));
-            Q.sd[si] = Real4<R>::make(s_d.x, s_d.y, s_d.z, R(0));
-            Q.sc[si] = Real4<R>::make(s_c.x, s_c.y, s_c.z, R(0));
+        int si = warp_append(Q.shadow_count + bounce, g.want_shadow);
+        if (g.want_shadow) {
+            st_stream(Q.so + si, Real4<R>::make(g.s_o.x, g.s_o.y, g.s_o.z, pack_int<R>((int64_t)slot)));
+            st_stream(Q.sd + si, Real4<R>::make(g.s_d.x, g.s_d.y, g.s_d.z, R(0)));
+            st_stream(Q.sc + si, Real4<R>::make(g.s_c.x, g.s_c.y, g.s_c.z, R(0)));
         }
-        int ni = warp_append(Q.ray_count + bounce + 1, alive);
-        if (alive) {
-            no[ni] = Real4<R>::make(new_o.x, new_o.y, new_o.z, pack_int<R>((int64_t)slot));
-            nd[ni] = Real4<R>::make(new_d.x, new_d.y, new_d.z, pack_int<R>((int64_t)rng));
-            nt[ni] = Real4<R>::make(thr.x, thr.y, thr.z, pack_int<R>((int64_t)(bounce + 1)));
+        int ni = warp_append(Q.ray_count + bounce + 1, g.alive);
+        if (g.alive) {
+            st_stream(no + ni, Real4<R>::make(g.new_o.x, g.new_o.y, g.new_o.z, pack_int<R>((int64_t)slot)));
+            st_stream(nd + ni, Real4<R>::make(g.new_d.x, g.new_d.y, g.new_d.z, pack_int<R>((int64_t)g.rng)));
+            st_stream(nt + ni, Real4<R>::make(g.thr.x, g.thr.y, g.thr.z, pack_int<R>((int64_t)(bounce + 1))));
         }
     }
 }
@@ -278,14 +307,14 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool lit = false;
         if (i < n) {
-            real4<R> a = Q.so[i], b = Q.sd[i];
+            real4<R> a = ld_stream(Q.so + i), b = ld_stream(Q.sd + i);
             Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
             Hit<R> h;
             lit = S.scan_incoherent ? !scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h)
                                     : !traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);   // :275-277
             if (lit) {
                 int slot = (int)unpack_u<R>(a.w);
-                real4<R> c = Q.sc[i], l = Q.L[slot];
+                real4<R> c = ld_stream(Q.sc + i), l = Q.L[slot];
                 Q.L[slot] = Real4<R>::make(l.x + c.x, l.y + c.y, l.z + c.z, l.w);
             }
         }

@@ -68,7 +68,7 @@ __device__ __forceinline__ bool hit_rect(const SceneDev &S, int i, const Ray<R> 
     V3<R> anchor = xyz<R>(r0), n = xyz<R>(r1);
     R denom = dot(n, r.d);
     if (CpuSem ? (abs_(denom) < R(1e-6)) : !(abs_(denom) > R(1e-6))) return false;
-    R t = dot(anchor - r.o, n) / denom;
+    R t = div_(dot(anchor - r.o, n), denom);
     if (CpuSem) {                                            // closed range (core/geometry.py:56)
         if (t < t_min || !(t < t_far || (allow_eq && t == t_far))) return false;
     } else {
@@ -100,12 +100,14 @@ __device__ __forceinline__ bool hit_sphere(const SceneDev &S, int i, const Ray<R
         // float32: c = |oc|^2 - r^2 cancels catastrophically from 50 units away;
         // b^2 - a*c == a * (r^2 - |oc - (b/a) d|^2) is the same quantity without the cancellation.
         r2 = s0.w * s0.w;
-        V3<R> perp = oc - r.d * (b / a);
+        V3<R> perp = oc - r.d * div_(b, a);
         disc = a * (r2 - dot(perp, perp));
     }
     if (!(disc > R(0))) return false;
     R sq = sqrt_(disc);
-    R t1 = (-b - sq) / a, t2 = (-b + sq) / a;
+    R t1, t2;
+    if constexpr (sizeof(R) == 4) { R ia = rcp_(a); t1 = (-b - sq) * ia; t2 = (-b + sq) * ia; }
+    else { t1 = (-b - sq) / a; t2 = (-b + sq) / a; }
     // nearest root beyond t_min, then the (t_min, t_far) range test — equals the reference's
     // "t1 if in range else t2 if in range" because t2 > t1
     R t;
@@ -125,6 +127,27 @@ __device__ __forceinline__ bool hit_tri(const SceneDev &S, int i, const Ray<R> &
     V3<R> v0 = xyz<R>(ldg4(q)), e1 = xyz<R>(ldg4(q + 1)), e2 = xyz<R>(ldg4(q + 2));
     V3<R> h = cross(r.d, e2);
     R a = dot(e1, h);
+    if constexpr (sizeof(R) == 4) {
+        // float32: every rejection test is done on the un-divided determinants (u = U/a, v = V/a,
+        // t = T/a; multiply the inequalities by |a|), so the division runs only for accepted hits and
+        // the common path is branch-free: ~30 FMA-class instructions per triangle.
+        V3<R> s = r.o - v0;
+        R U = dot(s, h);
+        V3<R> qq = cross(s, e1);
+        R V = dot(r.d, qq), T = dot(e2, qq);
+        R aa = abs_(a);
+        int sg = __float_as_int(a) & 0x80000000;
+        R Us = __int_as_float(__float_as_int(U) ^ sg), Vs = __int_as_float(__float_as_int(V) ^ sg),
+          Ts = __int_as_float(__float_as_int(T) ^ sg);
+        bool ok = !(aa < R(1e-6)) && Us >= R(0) && Us <= aa && Vs >= R(0) && Us + Vs <= aa &&
+                  Ts > t_min * aa && Ts <= t_far * aa;
+        if (!ok) return false;
+        R f = rcp_(a);
+        R t = f * T;
+        if (!(t_min < t && (t < t_far || (allow_eq && t == t_far)))) return false;
+        t_out = t; u_out = f * U; v_out = f * V;
+        return true;
+    }
     if (abs_(a) < R(1e-6)) return false;
     R f = R(1) / a;
     V3<R> s = r.o - v0;
@@ -188,7 +211,7 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
                                          Hit<R> &best) {
     best.t = t_max; best.prim = -1; best.a = R(0); best.b = R(0);
     if (S.n_prims == 0) return false;
-    V3<R> id = {R(1) / r.d.x, R(1) / r.d.y, R(1) / r.d.z};
+    V3<R> id = {rcp_(r.d.x), rcp_(r.d.y), rcp_(r.d.z)};
     int stack[kStackDepth];
     int sp = 0;
     int ref = S.root;
@@ -264,11 +287,11 @@ __device__ __forceinline__ void make_surface(const SceneDev &S, const Ray<R> &r,
         const real4<R> *q = reinterpret_cast<const real4<R> *>(S.rect) + 4 * h.prim;
         real4<R> r0 = ldg4(q), r1 = ldg4(q + 1);
         sf.n = xyz<R>(r1);
-        sf.u = h.a / r0.w; sf.v = h.b / r1.w;
+        sf.u = div_(h.a, r0.w); sf.v = div_(h.b, r1.w);
     } else if (h.prim < S.n_rect + S.n_sphere) {
         const real4<R> *q = reinterpret_cast<const real4<R> *>(S.sphere) + 2 * (h.prim - S.n_rect);
         real4<R> s0 = ldg4(q);
-        sf.n = (sf.p - xyz<R>(s0)) / s0.w;
+        sf.n = div3(sf.p - xyz<R>(s0), s0.w);
         sf.u = R(0); sf.v = R(0);
     } else {
         real4<R> nn = ldg4(sh), uva = ldg4(sh + 1), uvb = ldg4(sh + 2);
@@ -332,7 +355,7 @@ __device__ __forceinline__ Ray<R> camera_ray(const Cam<R> &c, R u, R v) {
                c.llc.y + u * c.hor.y + v * c.ver.y - c.origin.y,
                c.llc.z + u * c.hor.z + v * c.ver.z - c.origin.z};
     R l = length(d);
-    if (l > R(0)) d = d / l;
+    if (l > R(0)) d = div3(d, l);
     r.d = d;
     return r;
 }
