@@ -82,7 +82,13 @@ typedef struct b2rt_scene {
                                     packed order (every lane of a warp tests the same primitive: no SIMT
                                     divergence) instead of walking the LBVH — faster when n_prims is a few
                                     dozen (profiles/r1a: LBVH walk 3.8-11 of 32 lanes active)             */
-    int32_t reserved_;
+    int32_t n_scan_prims;        /* planar scan records below (0: the generic per-type tests are used)      */
+    /* Small-scene scan records, float32 only: every rectangle, triangle and coplanar triangle PAIR forming a
+     * parallelogram as one "plane + two edge planes" record of 4 float4:
+     *   (N.xyz, cN)  (n1.xyz, d1)  (n2.xyz, d2)  (umax, vmax, bits(kind<<28 | idA), bits(idB))
+     * t = (cN - N.o)/(N.d), P = o + t d, u = n1.P + d1, v = n2.P + d2;  kind 0 rectangle (u<=umax, v<=vmax),
+     * 1 triangle (u+v<=1), 2/3 parallelogram of triangles idA (u>=v) / idB, diagonal ties to A (2) or B (3). */
+    const void *d_scan_prims;
 } b2rt_scene;
 
 const char *b2rt_last_error(void);
@@ -113,7 +119,8 @@ int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri,
 int b2rt_primary_hits(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
                       double du, double dv, double t_min, double t_max, int32_t use_bvh,
                       int32_t *d_ids, double *d_t, void *stream);
-/* Explicit rays: d_o, d_d float64[3*n].  d_rec (optional) float64[9*n]: t, point(3), normal(3), uv(2). */
+/* Explicit rays: d_o, d_d float64[3*n].  d_rec (optional) float64[9*n]: t, point(3), normal(3), uv(2).
+ * use_bvh: 1 LBVH walk, 0 generic scan of all primitives, 2 small-scene scan records (d_scan_prims). */
 int b2rt_trace_rays(const b2rt_scene *scene, int32_t n, const double *d_o, const double *d_d,
                     double t_min, double t_max, int32_t any_hit, int32_t use_bvh,
                     int32_t *d_ids, double *d_rec, void *stream);

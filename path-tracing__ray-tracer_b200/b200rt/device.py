@@ -94,6 +94,15 @@ class DeviceScene:
         s.d_bvh_nodes, s.d_bvh_top = self.nodes.data_ptr(), self.top.data_ptr()
         s.n_bvh_top, s.bvh_root = self.n_top, self.root
         s.scan_incoherent = 1 if 0 < packed.n_prims <= scan_max_prims else 0
+        self.scan_prims = None
+        s.n_scan_prims, s.d_scan_prims = 0, None
+        if s.scan_incoherent and precision == _lib.P_F32 and packed.semantics == 0:
+            from .packer import build_scan_prims
+            rec = build_scan_prims(packed)
+            if 0 < rec.shape[0] // 4 <= 64:
+                with torch.cuda.device(dev):
+                    self.scan_prims = to_device(rec, dev)
+                s.n_scan_prims, s.d_scan_prims = rec.shape[0] // 4, self.scan_prims.data_ptr()
         self.struct = s
 
     def ref(self):

@@ -312,3 +312,64 @@ def pack_scene(scene, semantics: str = "numba", textures=None) -> PackedScene:
                        texels, tex_info, lights, order,
                        np.array(_v(lc)) if lc is not None else np.ones(3),
                        np.array(_v(am)) if am is not None else np.full(3, 0.5))
+
+
+def build_scan_prims(p: PackedScene, pair_tol: float = 1e-5) -> np.ndarray:
+    """Small-scene scan records (``b2rt_scene.d_scan_prims``): float32 [4*n, 4].
+
+    Every rectangle, triangle, and coplanar triangle PAIR ``(p0,p1,p2), (p0,p2,p3)`` with
+    ``p2 = p1 + p3 - p0`` (a parallelogram split along its diagonal, as ``_create_single_cube`` /
+    ``_create_canvas`` emit them, ``custom_scene_builder.py:356-366,470-476``) becomes one record
+    "plane + two edge planes":  t = (cN - N.o)/(N.d),  P = o + t d,  u = n1.P + d1,  v = n2.P + d2.
+    N is the unit normal for rectangles and e1 x e2 (un-normalised) for triangles, so the |N.d| > 1e-6
+    guard equals the reference's ``abs(denom)`` / ``abs(a)`` guards (``cuda_path_tracer.py:536,683``).
+    """
+    recs = []
+    R = p.rect.reshape(-1, 4, 4)
+    for i in range(p.n_rect):
+        anchor, ul = R[i, 0, :3], R[i, 0, 3]
+        n, vl = R[i, 1, :3], R[i, 1, 3]
+        uu, vv = R[i, 2, :3], R[i, 3, :3]
+        recs.append(([*n, n @ anchor], [*uu, -(uu @ anchor)], [*vv, -(vv @ anchor)], (ul, vl), 0, i, 0))
+    T = p.tri.reshape(-1, 3, 4)
+    base = p.n_rect + p.n_sphere
+    used = np.zeros(p.n_tri, dtype=bool)
+
+    def edge_planes(v0, e1, e2):
+        N = np.cross(e1, e2)
+        a1 = np.cross(e2, N); a1 = a1 / (e1 @ a1)
+        a2 = np.cross(N, e1); a2 = a2 / (e2 @ a2)
+        return N, a1, a2
+
+    for i in range(p.n_tri):
+        if used[i]:
+            continue
+        v0, e1, e2 = T[i, 0, :3], T[i, 1, :3], T[i, 2, :3]
+        scale = max(np.abs(v0).max(), np.abs(e1).max(), np.abs(e2).max(), 1e-30)
+        mate = -1
+        if p.n_tri <= 4096:                       # pairing is for small scenes; large ones walk the LBVH
+            for j in range(p.n_tri):
+                if j == i or used[j]:
+                    continue
+                w0, f1, f2 = T[j, 0, :3], T[j, 1, :3], T[j, 2, :3]
+                # j = (p0, p2, p3) with p2 = i.v2 and p3 = p0 + (e2_i - e1_i)
+                if np.abs(w0 - v0).max() <= pair_tol * scale and np.abs(f1 - e2).max() <= pair_tol * scale \
+                        and np.abs(f2 - (e2 - e1)).max() <= pair_tol * scale:
+                    mate = j
+                    break
+        used[i] = True
+        if mate >= 0:
+            used[mate] = True
+            eq1, eq2 = e1, T[mate, 2, :3]          # parallelogram edges p1-p0 and p3-p0
+            N, a1, a2 = edge_planes(v0, eq1, eq2)
+            kind = 2 if i < mate else 3            # diagonal ties go to the lower packed id
+            recs.append(([*N, N @ v0], [*a1, -(a1 @ v0)], [*a2, -(a2 @ v0)], (1.0, 1.0), kind, base + i, base + mate))
+        else:
+            N, a1, a2 = edge_planes(v0, e1, e2)
+            recs.append(([*N, N @ v0], [*a1, -(a1 @ v0)], [*a2, -(a2 @ v0)], (1.0, 1.0), 1, base + i, 0))
+    out = np.zeros((len(recs), 4, 4), dtype=np.float32)
+    for k, (q0, q1, q2, lim, kind, ida, idb) in enumerate(recs):
+        out[k, 0], out[k, 1], out[k, 2] = q0, q1, q2
+        out[k, 3, 0], out[k, 3, 1] = lim
+        out[k, 3, 2:4] = np.array([(kind << 28) | ida, idb], dtype=np.int32).view(np.float32)
+    return out.reshape(-1, 4)

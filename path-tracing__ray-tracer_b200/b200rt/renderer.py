@@ -354,7 +354,7 @@ def trace_rays(scene, origins, dirs, semantics="numba", precision="f64", t_min=0
         ids = torch.empty(n, dtype=torch.int32, device=device)
         rec = torch.empty(n * 9, dtype=torch.float64, device=device)
         _lib.check(lib.b2rt_trace_rays(ds.ref(), n, o.data_ptr(), d.data_ptr(), t_min, t_max, 1 if any_hit else 0,
-                                       1 if use_bvh else 0, ids.data_ptr(), rec.data_ptr(),
+                                       int(use_bvh), ids.data_ptr(), rec.data_ptr(),
                                        current_stream_ptr(device)), "b2rt_trace_rays")
         torch.cuda.synchronize(device)
         return ids.cpu().numpy(), rec.cpu().numpy().reshape(n, 9)

@@ -39,10 +39,11 @@ cudaError_t Api<R>::trace_rays(const b2rt_scene *s, int n, const double *o, cons
     SceneDev S = make_scene_dev(s);
     int T = 128;
     if (n <= 0) return cudaSuccess;
+    const size_t sm = use_bvh == 2 ? (size_t)S.n_scan * 64 + 64 : smem_top_bytes(S);
     if (S.semantics == B2RT_SEM_CPU)
-        trace_rays_kernel<R, true><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, n, o, d, R(t_min), R(t_max), any_hit, use_bvh, ids, rec);
+        trace_rays_kernel<R, true><<<(n + T - 1) / T, T, sm, st>>>(S, n, o, d, R(t_min), R(t_max), any_hit, use_bvh, ids, rec);
     else
-        trace_rays_kernel<R, false><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, n, o, d, R(t_min), R(t_max), any_hit, use_bvh, ids, rec);
+        trace_rays_kernel<R, false><<<(n + T - 1) / T, T, sm, st>>>(S, n, o, d, R(t_min), R(t_max), any_hit, use_bvh, ids, rec);
     return cudaGetLastError();
 }
 
@@ -111,6 +112,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     size_t counts_bytes = sizeof(int) * 2 * ((size_t)a.max_depth + 1) + 8;
 
     const size_t smem = smem_top_bytes(S);
+    const size_t smem_scan = (size_t)S.n_scan * 64;
+    const size_t smem_shadow = S.scan_incoherent ? smem_scan : smem;
     const int T = 256;
     static int g_extend = 0, g_shade = 0, g_shadow = 0, g_simple = 0;
     // persistent grids: resident CTAs per SM x SM count (a multiple of the 148 SMs)
@@ -118,8 +121,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     g_shade = persistent_grid((const void *)shade_kernel<R, Rng, 0>, T, 0);
     const bool fused = !(a.flags & 1);
     const int g_fuse_bvh = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem);
-    const int g_fuse_scan = persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, 0);
-    g_shadow = persistent_grid((const void *)shadow_kernel<R>, T, smem);
+    const int g_fuse_scan = persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, smem_scan);
+    g_shadow = persistent_grid((const void *)shadow_kernel<R>, T, smem_shadow);
     g_simple = persistent_grid((const void *)accumulate_kernel<R>, T, 0);
 
     if (std::is_same<Rng, RefRng>::value) {
@@ -140,7 +143,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             const bool scan = b > 0 && S.scan_incoherent;
             if (fused) {
                 prof_begin(kShade, st);
-                if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, 0, st>>>(S, Q, buf, b, a.max_depth);
+                if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth);
                 else shade_kernel<R, Rng, 1><<<g_fuse_bvh, T, smem, st>>>(S, Q, buf, b, a.max_depth);
                 prof_end(st);
                 launches -= 1;
@@ -153,7 +156,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 prof_end(st);
             }
             prof_begin(kShadow, st);
-            shadow_kernel<R><<<g_shadow, T, smem, st>>>(S, Q, b);
+            shadow_kernel<R><<<g_shadow, T, smem_shadow, st>>>(S, Q, b);
             prof_end(st);
             launches += 3;
             buf ^= 1;

@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(256)
 shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth) {
     extern __shared__ float4 s_top[];
     if (MODE == 1) stage_top(S, s_top);
+    const bool planar = MODE == 2 && sizeof(R) == 4 && S.n_scan > 0;      // s_top then holds the scan records
+    if (planar) stage_scan(S, s_top);
     const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
     real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
     int n = Q.ray_count[bounce];
@@ -277,7 +279,12 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth)
             } else if (MODE == 1) {
                 traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
             } else {
-                scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
+                if constexpr (sizeof(R) == 4) {
+                    if (planar) scan_small<false>(S, s_top, r, 0.001f, 1000000.0f, h);
+                    else scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
+                } else {
+                    scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
+                }
             }
             shade_segment<R, Rng>(S, Q, r, h, slot, bounce, max_depth, g);
         }
@@ -301,7 +308,9 @@ template <typename R>
 __global__ void __launch_bounds__(256)
 shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
     extern __shared__ float4 s_top[];
+    const bool planar = S.scan_incoherent && sizeof(R) == 4 && S.n_scan > 0;
     if (!S.scan_incoherent) stage_top(S, s_top);
+    else if (planar) stage_scan(S, s_top);
     int n = Q.shadow_count[bounce];
     int n_round = (n + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -310,8 +319,13 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
             real4<R> a = ld_stream(Q.so + i), b = ld_stream(Q.sd + i);
             Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
             Hit<R> h;
-            lit = S.scan_incoherent ? !scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h)
-                                    : !traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);   // :275-277
+            bool occluded;                                                          // :275-277 t_max = 1e6
+            if (!S.scan_incoherent) occluded = traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);
+            else if constexpr (sizeof(R) == 4) {
+                occluded = planar ? scan_small<true>(S, s_top, r, 0.001f, 1000000.0f, h)
+                                  : scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h);
+            } else occluded = scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h);
+            lit = !occluded;
             if (lit) {
                 int slot = (int)unpack_u<R>(a.w);
                 real4<R> c = ld_stream(Q.sc + i), l = Q.L[slot];

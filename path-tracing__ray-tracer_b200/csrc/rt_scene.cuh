@@ -26,6 +26,8 @@ struct SceneDev {
     const float4 *nodes, *top;
     int n_top, root;
     int scan_incoherent;
+    int n_scan;
+    const float4 *scan;
 };
 
 inline SceneDev make_scene_dev(const b2rt_scene *s) {
@@ -42,6 +44,8 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.top = reinterpret_cast<const float4 *>(s->d_bvh_top);
     d.n_top = s->n_bvh_top; d.root = s->bvh_root;
     d.scan_incoherent = s->scan_incoherent;
+    d.n_scan = s->precision == B2RT_PRECISION_F32 ? s->n_scan_prims : 0;
+    d.scan = reinterpret_cast<const float4 *>(s->d_scan_prims);
     return d;
 }
 
@@ -261,6 +265,59 @@ __device__ __forceinline__ bool scan_all(const SceneDev &S, const Ray<R> &r, R t
         if (AnyHit && best.prim >= 0) return true;
     }
     return best.prim >= 0;
+}
+
+// Small-scene scan over the planar records of b2rt_scene.d_scan_prims (float32 only) followed by the spheres.
+// Every lane of a warp tests the same record (uniform shared-memory reads, no stack, no per-type branch
+// inside the loop), and a parallelogram record covers two triangles: ~40 instructions per record instead
+// of ~65 per triangle for the generic Moeller-Trumbore test.  Same result contract as traverse():
+// closest t, ties to the lowest packed id.
+template <bool AnyHit>
+__device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, const Ray<float> &r, float t_min,
+                                           float t_max, Hit<float> &best) {
+    best.t = t_max; best.prim = -1; best.a = 0.f; best.b = 0.f;
+    const float ox = r.o.x, oy = r.o.y, oz = r.o.z, dx = r.d.x, dy = r.d.y, dz = r.d.z;
+    for (int k = 0; k < S.n_scan; ++k) {
+        const float4 q0 = sp[4 * k], q1 = sp[4 * k + 1], q2 = sp[4 * k + 2], q3 = sp[4 * k + 3];
+        float dn = q0.x * dx + q0.y * dy + q0.z * dz;
+        float T = q0.w - (q0.x * ox + q0.y * oy + q0.z * oz);
+        float t = __fdividef(T, dn);
+        float px = fmaf(t, dx, ox), py = fmaf(t, dy, oy), pz = fmaf(t, dz, oz);
+        float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
+        float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
+        const int w = __float_as_int(q3.z), kind = w >> 28;          // warp-uniform
+        int id = w & 0x0fffffff;
+        bool inside = u >= 0.f && v >= 0.f;
+        float a = u, b = v;
+        if (kind == 1) inside = inside && (u + v <= 1.f);
+        else inside = inside && u <= q3.x && v <= q3.y;
+        if (kind >= 2) {
+            bool first = kind == 2 ? (u >= v) : (u > v);
+            id = first ? id : __float_as_int(q3.w);
+            a = first ? u - v : u;
+            b = first ? v : v - u;
+        }
+        bool ok = inside && fabsf(dn) > 1e-6f && t > t_min && (t < best.t || (t == best.t && id < best.prim));
+        if (ok) {
+            best.t = t; best.prim = id; best.a = a; best.b = b;
+            if (AnyHit) return true;
+        }
+    }
+    for (int i = 0; i < S.n_sphere; ++i) {
+        int prim = S.n_rect + i;
+        float t;
+        bool allow_eq = best.prim >= 0 && prim < best.prim;
+        if (hit_sphere<float>(S, i, r, t_min, best.t, allow_eq, t)) {
+            best.t = t; best.prim = prim; best.a = 0.f; best.b = 0.f;
+            if (AnyHit) return true;
+        }
+    }
+    return best.prim >= 0;
+}
+
+__device__ __forceinline__ void stage_scan(const SceneDev &S, float4 *s_scan) {
+    for (int i = threadIdx.x; i < 4 * S.n_scan; i += blockDim.x) s_scan[i] = __ldg(S.scan + i);
+    __syncthreads();
 }
 
 // cooperative copy of the BVH top levels into shared memory (call from every thread of the CTA)

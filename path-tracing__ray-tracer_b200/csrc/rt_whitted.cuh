@@ -33,7 +33,8 @@ template <typename R, bool CpuSem>
 __global__ void __launch_bounds__(128)
 trace_rays_kernel(SceneDev S, int n, const double *o, const double *d, R t_min, R t_max, int any_hit, int use_bvh,
                   int *ids, double *rec) {
-    stage_top(S, smem_top);
+    const bool planar = use_bvh == 2 && sizeof(R) == 4 && S.n_scan > 0;
+    if (planar) stage_scan(S, smem_top); else stage_top(S, smem_top);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray<R> r;
@@ -41,7 +42,14 @@ trace_rays_kernel(SceneDev S, int n, const double *o, const double *d, R t_min, 
     r.d = {R(d[3 * i]), R(d[3 * i + 1]), R(d[3 * i + 2])};
     Hit<R> h;
     bool ok;
-    if (any_hit) ok = use_bvh ? traverse<R, CpuSem, true>(S, smem_top, r, t_min, t_max, h)
+    if constexpr (sizeof(R) == 4) {
+        if (planar) {
+            ok = any_hit ? scan_small<true>(S, smem_top, r, t_min, t_max, h) : scan_small<false>(S, smem_top, r, t_min, t_max, h);
+            use_bvh = -1;
+        }
+    }
+    if (use_bvh < 0) {}
+    else if (any_hit) ok = use_bvh ? traverse<R, CpuSem, true>(S, smem_top, r, t_min, t_max, h)
                               : scan_all<R, CpuSem, true>(S, r, t_min, t_max, h);
     else ok = use_bvh ? traverse<R, CpuSem, false>(S, smem_top, r, t_min, t_max, h)
                       : scan_all<R, CpuSem, false>(S, r, t_min, t_max, h);

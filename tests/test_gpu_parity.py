@@ -63,6 +63,21 @@ def test_scene_hit_rays_f32_close(scene, golden_dir):
     assert rel.max() < 2e-5
 
 
+def test_small_scene_scan_records_match_reference(scene, golden_dir):
+    """The float32 "plane + two edge planes" scan (13 parallelograms for the 26 triangles, 5 rectangles,
+    3 spheres) finds the same primitive as the reference's cuda_scene_hit on the golden rays."""
+    g = np.load(f"{golden_dir}/nb_scene_hit_rays.npz")
+    ids64, rec64 = renderer.trace_rays(scene, g["o"], g["d"], "numba", "f64")
+    ids, rec = renderer.trace_rays(scene, g["o"], g["d"], "numba", "f32", use_bvh=2)
+    same = ids == ids64
+    assert same.mean() > 0.997, f"{np.count_nonzero(~same)} of {same.size} ids differ"
+    both = same & (ids64 >= 0)
+    assert (np.abs(rec[both, 0] - rec64[both, 0]) / np.maximum(1.0, rec64[both, 0])).max() < 2e-5
+    assert np.abs(rec[both, 1:9] - rec64[both, 1:9]).max() < 2e-3          # point, normal, uv
+    occ, _ = renderer.trace_rays(scene, g["o"], g["d"], "numba", "f32", use_bvh=2, any_hit=True)
+    assert np.mean((occ >= 0) == (ids64 >= 0)) > 0.999
+
+
 def test_any_hit_matches_closest(scene, golden_dir):
     g = np.load(f"{golden_dir}/nb_scene_hit_rays.npz")
     ids, _ = renderer.trace_rays(scene, g["o"], g["d"], "numba", "f64")
