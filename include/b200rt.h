@@ -89,6 +89,10 @@ typedef struct b2rt_scene {
      * t = (cN - N.o)/(N.d), P = o + t d, u = n1.P + d1, v = n2.P + d2;  kind 0 rectangle (u<=umax, v<=vmax),
      * 1 triangle (u+v<=1), 2/3 parallelogram of triangles idA (u>=v) / idB, diagonal ties to A (2) or B (3). */
     const void *d_scan_prims;
+    /* Optional int32[n_lights]: for each light sample the scan record (k) or sphere (64 + i) that blocks the
+     * most shadow rays towards it, precomputed on the host (packer.build_occluder_hints).  The shade stage
+     * tests this one primitive before queueing a shadow ray: a hit answers the occlusion query exactly. */
+    const int32_t *d_occluder_hint;
 } b2rt_scene;
 
 const char *b2rt_last_error(void);
@@ -150,8 +154,9 @@ int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, 
  * d_pixel_rng (int64[H*W], caller-zeroed before sample 0... see DESIGN.md) carries the per-pixel state.
  * flags: B2RT_PATH_UNFUSED runs extend and shade as separate kernels through the hit stream (the default
  * fuses them: closest hit and shading in one kernel per bounce).
- * d_counters (optional) uint64[8], accumulated: [0] paths, [1] closest-hit rays, [2] shadow rays,
- * [3] unshadowed light samples, [4] kernel launches made by this call.
+ * d_counters (optional) uint64[8], accumulated: [0] paths, [1] closest-hit rays, [2] shadow rays answered
+ * (queued + resolved by the occluder cache), [3] unshadowed light samples, [4] kernel launches made by this
+ * call, [5] shadow rays resolved by the occluder cache without being queued.
  */
 int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
                      int32_t spp_local, int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth,

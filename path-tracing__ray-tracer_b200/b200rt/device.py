@@ -39,7 +39,7 @@ class DeviceScene:
 
     def __init__(self, packed: PackedScene, precision: int = _lib.P_F32, device=None,
                  top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
-                 scan_max_prims: int = SCAN_MAX_PRIMS):
+                 scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.packed = packed
@@ -95,7 +95,8 @@ class DeviceScene:
         s.n_bvh_top, s.bvh_root = self.n_top, self.root
         s.scan_incoherent = 1 if 0 < packed.n_prims <= scan_max_prims else 0
         self.scan_prims = None
-        s.n_scan_prims, s.d_scan_prims = 0, None
+        s.n_scan_prims, s.d_scan_prims, s.d_occluder_hint = 0, None, None
+        self.occluder_hint = None
         if s.scan_incoherent and precision == _lib.P_F32 and packed.semantics == 0:
             from .packer import build_scan_prims
             rec = build_scan_prims(packed)
@@ -103,6 +104,12 @@ class DeviceScene:
                 with torch.cuda.device(dev):
                     self.scan_prims = to_device(rec, dev)
                 s.n_scan_prims, s.d_scan_prims = rec.shape[0] // 4, self.scan_prims.data_ptr()
+                if occluder_hints and 0 < packed.lights.shape[0] <= 4096:
+                    from .packer import build_occluder_hints
+                    self.occluder_hint_host = build_occluder_hints(packed, rec)
+                    with torch.cuda.device(dev):
+                        self.occluder_hint = to_device(self.occluder_hint_host, dev)
+                    s.d_occluder_hint = self.occluder_hint.data_ptr()
         self.struct = s
 
     def ref(self):

@@ -373,3 +373,78 @@ def build_scan_prims(p: PackedScene, pair_tol: float = 1e-5) -> np.ndarray:
         out[k, 3, 0], out[k, 3, 1] = lim
         out[k, 3, 2:4] = np.array([(kind << 28) | ida, idb], dtype=np.int32).view(np.float32)
     return out.reshape(-1, 4)
+
+
+def build_occluder_hints(p: PackedScene, scan: np.ndarray, n_points: int = 4096, seed: int = 0) -> np.ndarray:
+    """For every light sample, the scan record (code k) or sphere (code 64 + i) that blocks the most
+    next-event shadow rays towards it -> int32 [n_lights] (-1: none).
+
+    Performance hint only (``b2rt_scene.d_occluder_hint``): the shade stage tests this one primitive
+    before queueing a shadow ray, and a hit answers the occlusion query exactly.  In the reference's
+    Cornell box the light samples sit at y = 14 *below* the ceiling at y = 15 and NEE shadow rays run to
+    t_max = 1e6 (``cuda_path_tracer.py:275-277``), so the ceiling blocks ~92 % of them.
+    Estimated here from area-weighted random surface points, both sides of every surface.
+    """
+    rng = np.random.default_rng(seed)
+    n_lights = p.lights.shape[0]
+    hints = np.full(max(1, n_lights), -1, dtype=np.int32)
+    rec = np.asarray(scan, dtype=np.float64).reshape(-1, 4, 4)
+    if n_lights == 0 or rec.shape[0] == 0:
+        return hints
+    pts, nrm, area = [], [], []
+    R = p.rect.reshape(-1, 4, 4)
+    for i in range(p.n_rect):
+        area.append(("r", i, R[i, 0, 3] * R[i, 1, 3]))
+    S = p.sphere.reshape(-1, 2, 4)
+    for i in range(p.n_sphere):
+        area.append(("s", i, 4 * np.pi * S[i, 0, 3] ** 2))
+    T = p.tri.reshape(-1, 3, 4)
+    for i in range(p.n_tri):
+        area.append(("t", i, 0.5 * np.linalg.norm(np.cross(T[i, 1, :3], T[i, 2, :3]))))
+    total = sum(a for _, _, a in area) or 1.0
+    for kind, i, a in area:
+        m = max(4, int(round(n_points * a / total)))
+        u, v = rng.random(m), rng.random(m)
+        if kind == "r":
+            P = R[i, 0, :3] + np.outer(u * R[i, 0, 3], R[i, 2, :3]) + np.outer(v * R[i, 1, 3], R[i, 3, :3])
+            N = np.tile(R[i, 1, :3], (m, 1))
+        elif kind == "s":
+            d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            P, N = S[i, 0, :3] + S[i, 0, 3] * d, d
+        else:
+            flip = u + v > 1
+            u, v = np.where(flip, 1 - u, u), np.where(flip, 1 - v, v)
+            P = T[i, 0, :3] + np.outer(u, T[i, 1, :3]) + np.outer(v, T[i, 2, :3])
+            n = np.cross(T[i, 1, :3], T[i, 2, :3]); n = n / (np.linalg.norm(n) or 1.0)
+            N = np.tile(n, (m, 1)) * np.where(rng.random(m) < 0.5, 1.0, -1.0)[:, None]
+        pts.append(P); nrm.append(N)
+    P, N = np.concatenate(pts), np.concatenate(nrm)
+    kinds = rec[:, 3, 2].astype(np.float32).view(np.int32) >> 28
+    for j in range(n_lights):
+        L = p.lights[j, :3]
+        d = L - P
+        dist = np.linalg.norm(d, axis=1)
+        ok = dist > 1e-3
+        d = d / np.where(ok, dist, 1.0)[:, None]
+        ok &= (d * N).sum(1) > 0                       # zero-payload shadow rays are never queued
+        o = P + 1e-3 * N
+        counts = {}
+        for k in range(rec.shape[0]):
+            q0, q1, q2, q3 = rec[k]
+            dn = d @ q0[:3]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t = (q0[3] - o @ q0[:3]) / dn
+            X = o + t[:, None] * d
+            u, v = X @ q1[:3] + q1[3], X @ q2[:3] + q2[3]
+            inside = (u >= 0) & (v >= 0) & ((u + v <= 1) if kinds[k] == 1 else ((u <= q3[0]) & (v <= q3[1])))
+            counts[k] = int((ok & inside & (np.abs(dn) > 1e-6) & (t > 1e-3) & (t < 1e6)).sum())
+        for i in range(p.n_sphere):
+            oc = o - S[i, 0, :3]
+            b = (oc * d).sum(1)
+            disc = b * b - ((oc * oc).sum(1) - S[i, 1, 0])
+            sq = np.sqrt(np.maximum(disc, 0))
+            hit = (disc > 0) & (((-b - sq) > 1e-3) | ((-b + sq) > 1e-3))
+            counts[64 + i] = int((ok & hit).sum())
+        best = max(counts, key=counts.get)
+        hints[j] = best if counts[best] > 0 else -1
+    return hints

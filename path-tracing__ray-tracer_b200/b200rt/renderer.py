@@ -60,9 +60,11 @@ class _TextureCache:
 class _B200Base(BaseRenderer):
     semantics = "numba"
 
-    def __init__(self, name: str, precision="f32", device=None, top_nodes: int = 512, scan_max_prims: int = 64):
+    def __init__(self, name: str, precision="f32", device=None, top_nodes: int = 512, scan_max_prims: int = 64,
+                 occluder_hints: bool = True):
         super().__init__(name)
         self.scan_max_prims = scan_max_prims
+        self.occluder_hints = occluder_hints
         try:
             self.device = require_cuda(device)
             self.lib = _lib.load()
@@ -79,7 +81,8 @@ class _B200Base(BaseRenderer):
         cam = pack_camera(camera, self.semantics)
         reach = float(np.abs(cam[:3]).max())
         ds = DeviceScene(packed, self.precision, self.device, self.top_nodes, ray_origin_extent=reach,
-                         textures_dev=dev_tex, scan_max_prims=self.scan_max_prims)
+                         textures_dev=dev_tex, scan_max_prims=self.scan_max_prims,
+                         occluder_hints=self.occluder_hints)
         ds.cam = cam
         ds.h2d_total = ds.h2d_bytes() - (0 if self._tex_cache.uploaded_bytes else
                                          ds.texels.numel() * ds.texels.element_size())
@@ -108,8 +111,8 @@ class B200PathTracer(_B200Base):
 
     def __init__(self, precision="f32", rng="pcg", seed: int = 0, spp_per_wave: Optional[int] = None,
                  device=None, top_nodes: int = 512, wave_paths: int = 1 << 24, scan_max_prims: int = 64,
-                 fused: bool = True):
-        super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims)
+                 fused: bool = True, occluder_hints: bool = True):
+        super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints)
         self.flags = 0 if fused else 1
         self.rng_mode = _RNG[rng]
         self.seed = int(seed)

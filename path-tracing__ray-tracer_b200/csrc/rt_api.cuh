@@ -80,7 +80,7 @@ template <typename R> struct PathLayout {
         size_t n = (size_t)W * H * spp_per_wave;
         L.stream_bytes = align256(n * sizeof(real4<R>));
         L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
-        L.total = L.counts_off + align256(sizeof(int) * (2 * (size_t)max_depth + 2) + 16);
+        L.total = L.counts_off + align256(sizeof(unsigned long long) * ((size_t)max_depth + 3));
         return L;
     }
 };
@@ -105,11 +105,11 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.ro[0] = stream_at(0); Q.rd[0] = stream_at(1); Q.th[0] = stream_at(2);
     Q.ro[1] = stream_at(3); Q.rd[1] = stream_at(4); Q.th[1] = stream_at(5);
     Q.hit = stream_at(6); Q.so = stream_at(7); Q.sd = stream_at(8); Q.sc = stream_at(9); Q.L = stream_at(10);
-    int *counts = (int *)(base + L.counts_off);
-    Q.ray_count = counts;
-    Q.shadow_count = counts + a.max_depth + 1;
-    Q.unshadowed = (unsigned long long *)(counts + 2 * (a.max_depth + 1));   // even int count: 8-byte aligned
-    size_t counts_bytes = sizeof(int) * 2 * ((size_t)a.max_depth + 1) + 8;
+    unsigned long long *counts = (unsigned long long *)(base + L.counts_off);
+    Q.counts = counts;
+    Q.unshadowed = counts + a.max_depth + 1;
+    Q.culled = counts + a.max_depth + 2;
+    size_t counts_bytes = sizeof(unsigned long long) * ((size_t)a.max_depth + 3);
 
     const size_t smem = smem_top_bytes(S);
     const size_t smem_scan = (size_t)S.n_scan * 64;
@@ -120,8 +120,11 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     g_extend = persistent_grid((const void *)extend_kernel<R>, T, smem);
     g_shade = persistent_grid((const void *)shade_kernel<R, Rng, 0>, T, 0);
     const bool fused = !(a.flags & 1);
-    const int g_fuse_bvh = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem);
-    const int g_fuse_scan = persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, smem_scan);
+    const size_t smem_bvh = smem + (S.scan_incoherent ? smem_scan : 0);
+    const int g_fuse_bvh = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem_bvh);
+    const bool planar = sizeof(R) == 4 && S.n_scan > 0;
+    const int g_fuse_scan = planar ? persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_scan)
+                                   : persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, 0);
     g_shadow = persistent_grid((const void *)shadow_kernel<R>, T, smem_shadow);
     g_simple = persistent_grid((const void *)accumulate_kernel<R>, T, 0);
 
@@ -143,13 +146,14 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             const bool scan = b > 0 && S.scan_incoherent;
             if (fused) {
                 prof_begin(kShade, st);
-                if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth);
-                else shade_kernel<R, Rng, 1><<<g_fuse_bvh, T, smem, st>>>(S, Q, buf, b, a.max_depth);
+                if (scan && planar) shade_kernel<R, Rng, 3><<<g_fuse_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth);
+                else if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, 0, st>>>(S, Q, buf, b, a.max_depth);
+                else shade_kernel<R, Rng, 1><<<g_fuse_bvh, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth);
                 prof_end(st);
                 launches -= 1;
             } else {
                 prof_begin(kExtend, st);
-                extend_kernel<R><<<g_extend, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.ray_count + b, scan ? 1 : 0);
+                extend_kernel<R><<<g_extend, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, scan ? 1 : 0);
                 prof_end(st);
                 prof_begin(kShade, st);
                 shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth);
@@ -166,7 +170,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         prof_end(st);
         ++launches;
         if (a.counters) {
-            path_counters_kernel<<<1, 1, 0, st>>>(Q.ray_count, Q.shadow_count, Q.unshadowed, a.max_depth,
+            path_counters_kernel<<<1, 1, 0, st>>>(Q.counts, Q.unshadowed, Q.culled, a.max_depth,
                                                   (long long)npix * k, launches + 1, a.counters);
         }
         if ((e = cudaGetLastError())) return e;

@@ -57,7 +57,11 @@ template <typename R> __device__ __forceinline__ R dot(V3<R> a, V3<R> b) { retur
 template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+// float32 production kernels use the single-instruction MUFU approximations (<= 1 ulp, no slow-path call:
+// the IEEE sequences cost ~10 instructions and a CALL each and pushed the fused kernel past the 32 KB
+// instruction cache); the float64 parity kernels keep IEEE sqrt and division.
+__device__ __forceinline__ float sqrt_(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
 __device__ __forceinline__ double abs_(double x) { return fabs(x); }
@@ -68,18 +72,17 @@ __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); 
 __device__ __forceinline__ float pow_(float a, float b) { return powf(a, b); }
 __device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
 // Division policy: the float64 parity instantiation divides exactly where the reference divides;
-// the float32 production instantiation multiplies by one correctly-rounded reciprocal (MUFU.RCP + fix-up)
-// instead of running the ~10-instruction IEEE division sequence per component.
+// the float32 production instantiation multiplies by one MUFU.RCP reciprocal.
 template <typename R> __device__ __forceinline__ R rcp_(R x) {
-    if constexpr (sizeof(R) == 4) return __frcp_rn(x);
+    if constexpr (sizeof(R) == 4) return rcp_approx(x);
     else return R(1) / x;
 }
 template <typename R> __device__ __forceinline__ V3<R> div3(V3<R> a, R k) {
-    if constexpr (sizeof(R) == 4) { R r = __frcp_rn(k); return {a.x * r, a.y * r, a.z * r}; }
+    if constexpr (sizeof(R) == 4) { R r = rcp_approx(k); return {a.x * r, a.y * r, a.z * r}; }
     else return {a.x / k, a.y / k, a.z / k};
 }
 template <typename R> __device__ __forceinline__ R div_(R a, R b) {
-    if constexpr (sizeof(R) == 4) return a * __frcp_rn(b);
+    if constexpr (sizeof(R) == 4) return a * rcp_approx(b);
     else return a / b;
 }
 template <typename R> __device__ __forceinline__ R length(V3<R> a) { return sqrt_(a.x * a.x + a.y * a.y + a.z * a.z); }

@@ -28,6 +28,7 @@ struct SceneDev {
     int scan_incoherent;
     int n_scan;
     const float4 *scan;
+    const int *occl_hint;
 };
 
 inline SceneDev make_scene_dev(const b2rt_scene *s) {
@@ -46,6 +47,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.scan_incoherent = s->scan_incoherent;
     d.n_scan = s->precision == B2RT_PRECISION_F32 ? s->n_scan_prims : 0;
     d.scan = reinterpret_cast<const float4 *>(s->d_scan_prims);
+    d.occl_hint = d.n_scan > 0 ? s->d_occluder_hint : nullptr;
     return d;
 }
 
@@ -272,9 +274,29 @@ __device__ __forceinline__ bool scan_all(const SceneDev &S, const Ray<R> &r, R t
 // inside the loop), and a parallelogram record covers two triangles: ~40 instructions per record instead
 // of ~65 per triangle for the generic Moeller-Trumbore test.  Same result contract as traverse():
 // closest t, ties to the lowest packed id.
+// Occluder codes (shadow-ray cache): k in [0, n_scan) = planar record k, 64 + i = sphere i.
+__device__ __forceinline__ bool occluder_test(const SceneDev &S, const float4 *sp, int code, const Ray<float> &r,
+                                              float t_min, float t_max) {
+    if (code < 0) return false;
+    if (code >= 64) {
+        float t;
+        return hit_sphere<float>(S, code - 64, r, t_min, t_max, false, t);
+    }
+    const float4 q0 = sp[4 * code], q1 = sp[4 * code + 1], q2 = sp[4 * code + 2], q3 = sp[4 * code + 3];
+    float dn = q0.x * r.d.x + q0.y * r.d.y + q0.z * r.d.z;
+    float T = q0.w - (q0.x * r.o.x + q0.y * r.o.y + q0.z * r.o.z);
+    float t = __fdividef(T, dn);
+    float px = fmaf(t, r.d.x, r.o.x), py = fmaf(t, r.d.y, r.o.y), pz = fmaf(t, r.d.z, r.o.z);
+    float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
+    float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
+    const int kind = __float_as_int(q3.z) >> 28;
+    bool inside = u >= 0.f && v >= 0.f && (kind == 1 ? (u + v <= 1.f) : (u <= q3.x && v <= q3.y));
+    return inside && fabsf(dn) > 1e-6f && t > t_min && t < t_max;
+}
+
 template <bool AnyHit>
 __device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, const Ray<float> &r, float t_min,
-                                           float t_max, Hit<float> &best) {
+                                           float t_max, Hit<float> &best, int *code_out = nullptr) {
     best.t = t_max; best.prim = -1; best.a = 0.f; best.b = 0.f;
     const float ox = r.o.x, oy = r.o.y, oz = r.o.z, dx = r.d.x, dy = r.d.y, dz = r.d.z;
     for (int k = 0; k < S.n_scan; ++k) {
@@ -300,7 +322,7 @@ __device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, 
         bool ok = inside && fabsf(dn) > 1e-6f && t > t_min && (t < best.t || (t == best.t && id < best.prim));
         if (ok) {
             best.t = t; best.prim = id; best.a = a; best.b = b;
-            if (AnyHit) return true;
+            if (AnyHit) { if (code_out) *code_out = k; return true; }
         }
     }
     for (int i = 0; i < S.n_sphere; ++i) {
@@ -309,7 +331,7 @@ __device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, 
         bool allow_eq = best.prim >= 0 && prim < best.prim;
         if (hit_sphere<float>(S, i, r, t_min, best.t, allow_eq, t)) {
             best.t = t; best.prim = prim; best.a = 0.f; best.b = 0.f;
-            if (AnyHit) return true;
+            if (AnyHit) { if (code_out) *code_out = 64 + i; return true; }
         }
     }
     return best.prim >= 0;
