@@ -133,22 +133,34 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         init_pixel_rng_kernel<<<(npix + 255) / 256, 256, 0, st>>>(W, H, (long long)a.seed, a.sample_offset, a.pixel_rng);
     }
     cudaError_t e;
+    // camera rays are generated inside the first bounce kernel when the RNG is counter-based
+    const bool fuse_primary = fused && std::is_same<Rng, PcgRng>::value;
+    const int g_primary = persistent_grid((const void *)shade_kernel<R, PcgRng, 4>, T, smem_bvh);
     for (int done = 0; done < a.spp_local; done += wave) {
         int k = a.spp_local - done < wave ? a.spp_local - done : wave;
         unsigned long long launches = 0;
+        PrimaryArgs<R> PA;
+        PA.cam = c; PA.W = W; PA.H = H; PA.spp_wave = k; PA.first_sample = a.sample_offset + done; PA.seed = a.seed;
         if ((e = cudaMemsetAsync(counts, 0, counts_bytes, st))) return e;
-        prof_begin(kRaygen, st);
-        raygen_kernel<R, Rng><<<g_simple, T, 0, st>>>(c, W, H, k, a.sample_offset + done, a.seed, a.pixel_rng, Q);
-        prof_end(st);
-        ++launches;
+        if (!fuse_primary) {
+            prof_begin(kRaygen, st);
+            raygen_kernel<R, Rng><<<g_simple, T, 0, st>>>(c, W, H, k, a.sample_offset + done, a.seed, a.pixel_rng, Q);
+            prof_end(st);
+            ++launches;
+        }
         int buf = 0;
         for (int b = 0; b < a.max_depth; ++b) {
             const bool scan = b > 0 && S.scan_incoherent;
-            if (fused) {
+            if (b == 0 && fuse_primary) {
                 prof_begin(kShade, st);
-                if (scan && planar) shade_kernel<R, Rng, 3><<<g_fuse_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth);
-                else if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, 0, st>>>(S, Q, buf, b, a.max_depth);
-                else shade_kernel<R, Rng, 1><<<g_fuse_bvh, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth);
+                shade_kernel<R, PcgRng, 4><<<g_primary, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth, PA);
+                prof_end(st);
+                launches -= 1;
+            } else if (fused) {
+                prof_begin(kShade, st);
+                if (scan && planar) shade_kernel<R, Rng, 3><<<g_fuse_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth, PA);
+                else if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);
+                else shade_kernel<R, Rng, 1><<<g_fuse_bvh, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth, PA);
                 prof_end(st);
                 launches -= 1;
             } else {
@@ -156,7 +168,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 extend_kernel<R><<<g_extend, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, scan ? 1 : 0);
                 prof_end(st);
                 prof_begin(kShade, st);
-                shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth);
+                shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);
                 prof_end(st);
             }
             prof_begin(kShadow, st);

@@ -185,16 +185,22 @@ template <typename R> struct Segment {       // what one loop iteration of cuda_
 
 // One loop iteration of cuda_trace_path (:229-469) for one path: sky / texture / NEE shadow-ray
 // emission / Russian roulette / BSDF sampling.  thr and rng come in through g and are updated.
-template <typename R, typename Rng>
+template <typename R, typename Rng, bool FIRST>
 __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueues<R> &Q, const float4 *s_scan,
                                               const Ray<R> &r, const Hit<R> &h, int slot, int bounce, int max_depth,
                                               Segment<R> &g) {
     V3<R> &thr = g.thr, &new_o = g.new_o, &new_d = g.new_d, &s_o = g.s_o, &s_d = g.s_d, &s_c = g.s_c;
     uint64_t &rng = g.rng;
     bool &alive = g.alive, &want_shadow = g.want_shadow;
+    if (FIRST) {                                                            // first touch of L[slot]
+        R sky = h.prim < 0 ? R(0.1) : R(0);
+        Q.L[slot] = Real4<R>::make(sky, sky, sky, R(0));
+    }
     if (h.prim < 0) {                                                       // :234-239 sky
-        real4<R> l = Q.L[slot];
-        Q.L[slot] = Real4<R>::make(l.x + thr.x * R(0.1), l.y + thr.y * R(0.1), l.z + thr.z * R(0.1), l.w);
+        if (!FIRST) {
+            real4<R> l = Q.L[slot];
+            Q.L[slot] = Real4<R>::make(l.x + thr.x * R(0.1), l.y + thr.y * R(0.1), l.z + thr.z * R(0.1), l.w);
+        }
     } else {
         Surface<R> sf;
         make_surface<R, false>(S, r, h, sf);
@@ -287,25 +293,35 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
     }
 }
 
+template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fused into the first bounce
+    Cam<R> cam;
+    int W, H, spp_wave;
+    long long first_sample;
+    unsigned long long seed;
+};
+
 // MODE 0: wavefront "shade" stage reading the hit stream written by extend_kernel.
+// MODE 4: bounce 0 with the counter-based RNG — the camera ray is generated in-register (no raygen kernel,
+// no 64 B/path queue round trip), walked through the LBVH and shaded; L[slot] is initialised here.
 // MODE 1/2/3: fused extend+shade — the closest hit is found in-register (1: LBVH walk, 2: warp-uniform scan of
 // all primitives with the generic tests, 3: the float32 planar scan records) and shaded at once, so the FP32-issue-bound intersection work overlaps the
 // latency-bound shading loads in one kernel and the hit stream (32 B/segment) never touches HBM.
 template <typename R, typename Rng, int MODE>
 __global__ void __launch_bounds__(256)
-shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth) {
+shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth, PrimaryArgs<R> P) {
     extern __shared__ float4 s_top[];
-    if (MODE == 1) stage_top(S, s_top);
+    if (MODE == 1 || MODE == 4) stage_top(S, s_top);
     if (MODE == 3) stage_scan(S, s_top);         // s_top then holds the scan records
     // scan records for the occluder cache: behind the BVH top copy in MODE 1, the records themselves in MODE 2
     const float4 *s_scan = nullptr;
     if (sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && S.occl_hint) {
-        if (MODE == 1) { stage_scan(S, s_top + 4 * S.n_top); s_scan = s_top + 4 * S.n_top; }
+        if (MODE == 1 || MODE == 4) { stage_scan(S, s_top + 4 * S.n_top); s_scan = s_top + 4 * S.n_top; }
         else if (MODE == 3) s_scan = s_top;
     }
     const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
     real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
-    int n = ray_count(Q, bounce);
+    int n = MODE == 4 ? P.W * P.H * P.spp_wave : ray_count(Q, bounce);
+    if (MODE == 4 && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)n;   // for the ray statistics
     int n_round = (n + 31) & ~31;                // whole warps iterate together (ballots in warp_append2)
     unsigned n_culled = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -314,23 +330,34 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth)
         g.alive = false; g.want_shadow = false; g.culled = false; g.rng = 0; g.light = 0;
         int slot = 0;
         if (valid) {
-            real4<R> a = ld_stream(ro + i), b = ld_stream(rd + i), c = ld_stream(th + i);
-            Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
-            slot = (int)unpack_u<R>(a.w);
-            g.rng = unpack_u<R>(b.w);
-            g.thr = xyz<R>(c);
+            Ray<R> r;
+            if (MODE == 4) {                     // cuda_path_trace_kernel's sample set-up (:35-41)
+                const int npix = P.W * P.H, pix = i % npix, s = i / npix;
+                const int x = pix % P.W, y = pix / P.W;
+                uint64_t state = PcgRng::seed((uint32_t)pix, (uint64_t)(P.first_sample + s), P.seed);
+                R rnd = PcgRng::template random<R>(state);
+                state = PcgRng::advance(state);
+                r = camera_ray<R>(P.cam, (R(x) + rnd) / R(P.W), (R(y) + rnd) / R(P.H));
+                slot = i; g.rng = state; g.thr = {R(1), R(1), R(1)};
+            } else {
+                real4<R> a = ld_stream(ro + i), b = ld_stream(rd + i), c = ld_stream(th + i);
+                r.o = xyz<R>(a); r.d = xyz<R>(b);
+                slot = (int)unpack_u<R>(a.w);
+                g.rng = unpack_u<R>(b.w);
+                g.thr = xyz<R>(c);
+            }
             Hit<R> h;
             if (MODE == 0) {
                 real4<R> hrec = ld_stream(Q.hit + i);
                 h.t = hrec.x; h.prim = (int)(long long)real_as_int(hrec.y); h.a = hrec.z; h.b = hrec.w;
-            } else if (MODE == 1) {
+            } else if (MODE == 1 || MODE == 4) {
                 traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
             } else if (MODE == 2) {
                 scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
             } else {
                 if constexpr (sizeof(R) == 4) scan_small<false>(S, s_top, r, 0.001f, 1000000.0f, h);
             }
-            shade_segment<R, Rng>(S, Q, s_scan, r, h, slot, bounce, max_depth, g);
+            shade_segment<R, Rng, MODE == 4>(S, Q, s_scan, r, h, slot, bounce, max_depth, g);
         }
         n_culled += g.culled ? 1u : 0u;
         int si, ni;
