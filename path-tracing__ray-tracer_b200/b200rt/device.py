@@ -24,14 +24,72 @@ def current_stream_ptr(device) -> int:
     return int(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _Staging:
+    """Per-device pinned staging buffer, grown on demand and reused by every upload (cudaHostAlloc is slow:
+    allocating pinned memory per array used to cost more than the copies themselves)."""
+
+    _pool = {}
+
+    @classmethod
+    def get(cls, device, nbytes: int) -> torch.Tensor:
+        key = str(device)
+        buf, ev = cls._pool.get(key, (None, None))
+        if ev is not None:
+            ev.synchronize()                      # the previous async copy out of this buffer has finished
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        cls._pool[key] = (buf, None)
+        return buf
+
+    @classmethod
+    def mark(cls, device) -> None:
+        key = str(device)
+        buf, _ = cls._pool[key]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        cls._pool[key] = (buf, ev)
+
+
+class Blob:
+    """Collects host arrays, ships them with ONE pinned H2D copy, hands back 256-byte-aligned device views."""
+
+    def __init__(self):
+        self.items, self.size = [], 0
+
+    def add(self, name: str, arr: np.ndarray) -> None:
+        arr = np.ascontiguousarray(arr)
+        off = (self.size + 255) & ~255
+        self.items.append((name, arr, off))
+        self.size = off + max(arr.nbytes, 16)
+
+    def upload(self, device) -> dict:
+        total = (self.size + 255) & ~255
+        host = _Staging.get(device, total)
+        hv = host.numpy()
+        for _, arr, off in self.items:
+            if arr.nbytes:
+                hv[off:off + arr.nbytes] = arr.reshape(-1).view(np.uint8)
+        dev = torch.empty(total, dtype=torch.uint8, device=device)
+        dev.copy_(host[:total], non_blocking=True)
+        _Staging.mark(device)
+        out = {"_blob": dev}
+        for name, arr, off in self.items:
+            n = max(arr.nbytes, 16)
+            view = dev[off:off + n].view(_TORCH_DTYPE[arr.dtype.str])
+            out[name] = view[:arr.size] if arr.nbytes else view[:0]
+        self.nbytes = total
+        return out
+
+
+_TORCH_DTYPE = {"<f4": torch.float32, "<f8": torch.float64, "<i4": torch.int32, "<u4": torch.int32, "|u1": torch.uint8,
+                "<i8": torch.int64}
+
+
 def to_device(arr: np.ndarray, device, pinned: bool = True) -> torch.Tensor:
-    """One H2D copy through pinned memory (the only way scene bytes reach HBM)."""
-    t = torch.from_numpy(np.ascontiguousarray(arr))
-    if t.numel() == 0:
-        return torch.zeros(max(1, 4), dtype=t.dtype, device=device)[:0].contiguous()
-    if pinned:
-        t = t.pin_memory()
-    return t.to(device, non_blocking=True)
+    """One H2D copy through the pinned staging buffer."""
+    b = Blob()
+    b.add("x", arr)
+    return b.upload(device)["x"]
 
 
 class DeviceScene:
@@ -47,24 +105,35 @@ class DeviceScene:
         real = np.float64 if precision == _lib.P_F64 else np.float32
         dev = self.device
         with torch.cuda.device(dev):
-            self.rect = to_device(packed.rect.astype(real), dev)
-            self.sphere = to_device(packed.sphere.astype(real), dev)
-            self.tri = to_device(packed.tri.astype(real), dev)
-            self.shade = to_device(packed.shade.astype(real), dev)
-            self.mat = to_device(packed.mat.astype(real), dev)
-            self.lights = to_device(packed.lights.astype(real), dev)
-            self.prim_mat = to_device(packed.prim_mat, dev)
-            self.mat_tex = to_device(packed.mat_tex, dev)
+            blob = Blob()
+            for name in ("rect", "sphere", "tri", "shade", "mat", "lights"):
+                blob.add(name, getattr(packed, name).astype(real))
+            blob.add("prim_mat", packed.prim_mat)
+            blob.add("mat_tex", packed.mat_tex)
+            if precision == _lib.P_F64:          # the LBVH builder always consumes float32 geometry
+                for name in ("rect", "sphere", "tri"):
+                    blob.add("g_" + name, getattr(packed, name).astype(np.float32))
+            if textures_dev is None:
+                blob.add("texels", packed.texels.view(np.int32))
+                blob.add("tex_info", packed.tex_info if packed.n_tex else np.zeros((1, 4), np.int32))
+            self.scan_host = self.occluder_hint_host = None
+            scan_ok = 0 < packed.n_prims <= scan_max_prims
+            if scan_ok and precision == _lib.P_F32 and packed.semantics == 0:
+                self.scan_host, self.occluder_hint_host = _small_scene_records(packed, occluder_hints)
+                if self.scan_host is not None:
+                    blob.add("scan", self.scan_host)
+                    if self.occluder_hint_host is not None:
+                        blob.add("hint", self.occluder_hint_host)
+            d = blob.upload(dev)
+            self._blob, self.h2d_small = d["_blob"], blob.nbytes
+            self.rect, self.sphere, self.tri, self.shade = d["rect"], d["sphere"], d["tri"], d["shade"]
+            self.mat, self.lights, self.prim_mat, self.mat_tex = d["mat"], d["lights"], d["prim_mat"], d["mat_tex"]
             if textures_dev is not None:
                 self.texels, self.tex_info = textures_dev
             else:
-                self.texels = to_device(packed.texels.view(np.int32), dev)
-                self.tex_info = to_device(packed.tex_info if packed.n_tex else np.zeros((1, 4), np.int32), dev)
-            # the builder always consumes float32 geometry
+                self.texels, self.tex_info = d["texels"], d["tex_info"]
             if precision == _lib.P_F64:
-                g_rect = to_device(packed.rect.astype(np.float32), dev)
-                g_sphere = to_device(packed.sphere.astype(np.float32), dev)
-                g_tri = to_device(packed.tri.astype(np.float32), dev)
+                g_rect, g_sphere, g_tri = d["g_rect"], d["g_sphere"], d["g_tri"]
             else:
                 g_rect, g_sphere, g_tri = self.rect, self.sphere, self.tri
             n = packed.n_prims
@@ -93,29 +162,41 @@ class DeviceScene:
         s.d_texels, s.d_tex_info, s.d_lights = self.texels.data_ptr(), self.tex_info.data_ptr(), self.lights.data_ptr()
         s.d_bvh_nodes, s.d_bvh_top = self.nodes.data_ptr(), self.top.data_ptr()
         s.n_bvh_top, s.bvh_root = self.n_top, self.root
-        s.scan_incoherent = 1 if 0 < packed.n_prims <= scan_max_prims else 0
-        self.scan_prims = None
+        s.scan_incoherent = 1 if scan_ok else 0
         s.n_scan_prims, s.d_scan_prims, s.d_occluder_hint = 0, None, None
-        self.occluder_hint = None
-        if s.scan_incoherent and precision == _lib.P_F32 and packed.semantics == 0:
-            from .packer import build_scan_prims
-            rec = build_scan_prims(packed)
-            if 0 < rec.shape[0] // 4 <= 64:
-                with torch.cuda.device(dev):
-                    self.scan_prims = to_device(rec, dev)
-                s.n_scan_prims, s.d_scan_prims = rec.shape[0] // 4, self.scan_prims.data_ptr()
-                if occluder_hints and 0 < packed.lights.shape[0] <= 4096:
-                    from .packer import build_occluder_hints
-                    self.occluder_hint_host = build_occluder_hints(packed, rec)
-                    with torch.cuda.device(dev):
-                        self.occluder_hint = to_device(self.occluder_hint_host, dev)
-                    s.d_occluder_hint = self.occluder_hint.data_ptr()
+        if self.scan_host is not None:
+            self.scan_prims = d["scan"]
+            s.n_scan_prims, s.d_scan_prims = self.scan_host.shape[0] // 4, self.scan_prims.data_ptr()
+            if self.occluder_hint_host is not None:
+                self.occluder_hint = d["hint"]
+                s.d_occluder_hint = self.occluder_hint.data_ptr()
         self.struct = s
 
     def ref(self):
         return C.byref(self.struct)
 
     def h2d_bytes(self) -> int:
-        ts = [self.rect, self.sphere, self.tri, self.shade, self.mat, self.lights, self.prim_mat, self.mat_tex,
-              self.texels, self.tex_info]
-        return int(sum(t.numel() * t.element_size() for t in ts))
+        return int(self.h2d_small)
+
+
+_small_cache: dict = {}
+
+
+def _small_scene_records(packed: PackedScene, want_hints: bool):
+    """Scan records + occluder hints, cached on the bytes of the packed geometry (pure functions of it)."""
+    import hashlib
+    from .packer import build_occluder_hints, build_scan_prims
+    h = hashlib.blake2b(digest_size=16)
+    for a in (packed.rect, packed.sphere, packed.tri, packed.lights):
+        h.update(np.ascontiguousarray(a).tobytes())
+    key = (h.hexdigest(), bool(want_hints))
+    if key not in _small_cache:
+        rec = build_scan_prims(packed)
+        if not (0 < rec.shape[0] // 4 <= 64):
+            _small_cache[key] = (None, None)
+        else:
+            hints = build_occluder_hints(packed, rec) if (want_hints and 0 < packed.lights.shape[0] <= 4096) else None
+            _small_cache[key] = (rec, hints)
+        if len(_small_cache) > 64:
+            _small_cache.pop(next(iter(_small_cache)))
+    return _small_cache[key]

@@ -179,6 +179,8 @@ def pack_scene(scene, semantics: str = "numba", textures=None) -> PackedScene:
     if textures is None:
         textures = pack_textures(scene)
     texels, tex_info, tex_id = textures
+    if texels is None:                       # textures live on the device already (renderer._TextureCache)
+        texels = np.zeros(1, dtype=np.uint32)
     mats = _Materials()
 
     def rnd(a):
