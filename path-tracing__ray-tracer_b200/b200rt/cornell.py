@@ -144,6 +144,16 @@ class CustomSceneBuilder:
                               reflective=0.1, refractive=0.85, ior=1.5),
         }
 
+    def _create_wall_materials(self) -> Dict[str, Material]:
+        wall = dict(diffuse=0.8, specular=0.1)
+        return {
+            "floor": Material(color=Vec3(0.9, 0.9, 0.9), **wall),
+            "back": Material(color=Vec3(0.9, 0.9, 0.9), **wall),
+            "left": Material(color=Vec3(255 / 255, 105 / 255, 180 / 255), **wall),
+            "right": Material(color=Vec3(52 / 255, 157 / 255, 204 / 255), **wall),
+            "ceiling": Material(color=Vec3(0.9, 0.9, 0.9), **wall),
+        }
+
     def _create_walls(self, scene: Scene, mats) -> None:
         s, h = self.box_size, self.box_size / 2.0
         # (material, anchor, normal, u_dir, v_dir)
