@@ -47,31 +47,34 @@ def is_stale() -> bool:
     return not os.path.isfile(LIB_PATH) or os.path.getmtime(LIB_PATH) < _sources_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """``defines``/``out`` build an experimental variant (e.g. ("-DB2RT_SCAN_UNROLL=2",)) next to the default."""
+    lib_path = out or LIB_PATH
+    if not force and not defines and not is_stale():
         return LIB_PATH
+    tag = "" if not defines else "_" + "_".join(d.replace("-D", "").replace("=", "") for d in defines)
     os.makedirs(BUILD, exist_ok=True)
     exe = nvcc()
     objs, procs = [], []
     for src, extra in UNITS:
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [exe, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(BUILD, src.replace(".cu", tag + ".o"))
+        cmd = [exe, *ARCH, *COMMON, *extra, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
-        out, _ = p.communicate()
-        if verbose and out:
-            print(out)
+        log, _ = p.communicate()
+        if verbose and log:
+            print(log)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    link = [exe, *ARCH, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+            raise RuntimeError(f"nvcc failed on {src}:\n{log}")
+    link = [exe, *ARCH, "-shared", "-o", lib_path, *objs, "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -307,7 +307,7 @@ template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fu
 // all primitives with the generic tests, 3: the float32 planar scan records) and shaded at once, so the FP32-issue-bound intersection work overlaps the
 // latency-bound shading loads in one kernel and the hit stream (32 B/segment) never touches HBM.
 template <typename R, typename Rng, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(R) != 4 ? 1 : (MODE == 3 ? B2RT_BOUNCE_MIN_BLOCKS : B2RT_BVH_MIN_BLOCKS))
 shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth, PrimaryArgs<R> P) {
     extern __shared__ float4 s_top[];
     if (MODE == 1 || MODE == 4) stage_top(S, s_top);

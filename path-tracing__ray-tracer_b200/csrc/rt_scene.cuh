@@ -13,7 +13,17 @@
 
 namespace b2rt {
 
-constexpr int kStackDepth = 64;       // LBVH depth bound: 30 Morton bits + log2(duplicates)
+#ifndef B2RT_SCAN_UNROLL
+#define B2RT_SCAN_UNROLL 2
+#endif
+#ifndef B2RT_BOUNCE_MIN_BLOCKS
+#define B2RT_BOUNCE_MIN_BLOCKS 4      // resident CTAs/SM requested for the float32 planar-scan bounce kernel (64 regs)
+#endif
+#ifndef B2RT_BVH_MIN_BLOCKS
+#define B2RT_BVH_MIN_BLOCKS 4         // ... for the float32 LBVH-walk bounce kernels (measured 6729 vs 6600 Mpaths/s with 3)
+#endif
+constexpr int kStackDepth = 64;
+constexpr int kScanUnroll = B2RT_SCAN_UNROLL;       // LBVH depth bound: 30 Morton bits + log2(duplicates)
 
 struct SceneDev {
     int n_rect, n_sphere, n_tri, n_prims;
@@ -299,6 +309,7 @@ __device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, 
                                            float t_max, Hit<float> &best, int *code_out = nullptr) {
     best.t = t_max; best.prim = -1; best.a = 0.f; best.b = 0.f;
     const float ox = r.o.x, oy = r.o.y, oz = r.o.z, dx = r.d.x, dy = r.d.y, dz = r.d.z;
+#pragma unroll kScanUnroll
     for (int k = 0; k < S.n_scan; ++k) {
         const float4 q0 = sp[4 * k], q1 = sp[4 * k + 1], q2 = sp[4 * k + 2], q3 = sp[4 * k + 3];
         float dn = q0.x * dx + q0.y * dy + q0.z * dz;
