@@ -361,7 +361,8 @@ def primary_hits(scene, camera, width, height, semantics="numba", precision="f64
                                          current_stream_ptr(device)), "b2rt_primary_hits")
         torch.cuda.synchronize(device)
         pid = ids.cpu().numpy().reshape(height, width)
-        obj = np.where(pid >= 0, packed.order[np.maximum(pid, 0), 0], -1).astype(np.int32)
+        order = packed.order[:, 0] if packed.order.shape[0] else np.zeros(1, dtype=np.int32)
+        obj = np.where(pid >= 0, order[np.maximum(pid, 0)], -1).astype(np.int32)
         return obj, tt.cpu().numpy().reshape(height, width), pid
 
 

@@ -1,0 +1,166 @@
+"""GPU parity beyond the Cornell box: random scenes, degenerate scenes, ragged sizes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import random_scenes as RS  # noqa: E402
+from b200rt import packer, renderer  # noqa: E402
+from b200rt.scene_api import Camera, Material, Plane, RenderSettings, Scene, Sphere, Triangle, Vec3  # noqa: E402
+from oracle import cpu_oracle as O  # noqa: E402
+
+
+def _rays(n, seed):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(-10, 10, (n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_scene_intersection_bit_exact(seed):
+    scene, cam = RS.make_scene(RS.local_api(), seed)
+    pk = O.nb_pack(scene, cam)
+    o, d = _rays(4000, seed)
+    ref_ids, ref = O.nb_scene_hit_rays(pk, o, d)
+    for use_bvh in (1, 0):
+        ids, rec = renderer.trace_rays(scene, o, d, "numba", "f64", use_bvh=use_bvh)
+        assert np.array_equal(ids, ref_ids)
+        hit = ids >= 0
+        assert np.array_equal(rec[hit], ref[hit][:, :9])
+    # float32 kernels (LBVH walk and the small-scene scan records): same primitive, close distance
+    for mode in (1, 2):
+        ids32, rec32 = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=mode)
+        same = ids32 == ref_ids
+        assert same.mean() > 0.995, (mode, np.count_nonzero(~same))
+        both = same & (ref_ids >= 0)
+        assert (np.abs(rec32[both, 0] - ref[both, 0]) / np.maximum(1, ref[both, 0])).max() < 5e-5
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_scene_renderers_match_oracle(seed):
+    scene, cam = RS.make_scene(RS.local_api(), seed)
+    pk = O.nb_pack(scene, cam)
+    W, H = 48, 36
+    # path tracer, float64 + reference RNG: exact replay
+    ref = O.nb_path_trace(pk, W, H, 6, 6, 0)
+    r = renderer.B200PathTracer(precision="f64", rng="reference", spp_per_wave=4)
+    acc, cnt = r.render_accum(scene, cam, RenderSettings(W, H, 6, 6))
+    ok = np.isclose(acc[..., :3], ref["sum"], rtol=1e-9, atol=1e-12).all(axis=2)
+    assert ok.mean() >= 0.99, np.count_nonzero(~ok)
+    # textured Whitted
+    u8_ref, f_ref, _ = O.nb_whitted_texture(pk, W, H, 4, 8)
+    f, u8 = renderer.B200TextureRaytracer(precision="f64").render_float(scene, cam, RenderSettings(W, H, 4, 8))
+    assert np.abs(f - f_ref).max() <= 1e-4
+    assert np.count_nonzero(u8 != u8_ref) <= 3
+    # CPU-renderer semantics through the reference BVH vs the LBVH
+    ref_cpu = O.cpu_whitted(O.cpu_export(scene, cam), W, H, 3)["rgb"]
+    rgb = renderer.B200WhittedRenderer(precision="f64", jitter_seed=None).trace(scene, cam, W, H, 3)
+    assert np.abs(rgb - ref_cpu).max() <= 1e-4
+
+
+def test_random_scene_f32_production_statistics():
+    """float32 + PCG + small-scene scan records + occluder hints on a scene with skewed rectangles and
+    unpaired triangles: same Monte-Carlo tolerance as the Cornell test."""
+    scene, cam = RS.make_scene(RS.local_api(), 12)
+    W, H, D, n = 64, 48, 6, 1024
+    ref = O.nb_path_trace(O.nb_pack(scene, cam), W, H, n, D)
+    m_ref = ref["sum"] / n
+    v_ref = np.maximum(ref["sumsq"] / n - m_ref ** 2, 0) * n / (n - 1)
+    acc, cnt, sq = renderer.B200PathTracer(precision="f32", seed=5).render_accum(scene, cam, RenderSettings(W, H, n, D), want_sumsq=True)
+    m = acc[..., :3].astype(np.float64) / n
+    v = np.maximum(sq[..., :3].astype(np.float64) / n - m ** 2, 0) * n / (n - 1)
+    lit = (v_ref > 1e-12) & (v > 1e-12)
+    s2 = (v_ref + v) / n
+    z2 = (m - m_ref) ** 2 / np.where(lit, s2, 1)
+    assert 0.75 < z2[lit].mean() < 1.3, z2[lit].mean()
+    assert (np.abs(m - m_ref)[lit] <= 3 * np.sqrt(s2[lit])).mean() >= 0.99
+    assert abs(m.mean() - m_ref.mean()) / m_ref.mean() < 0.03
+    ref_rpp = (ref["counters"]["closest_rays"] + ref["counters"]["shadow_rays"]) / (W * H * n)
+    # shadow rays with an exactly-zero payload are never traced, so the GPU count is a little lower
+    assert 0.8 * ref_rpp < (cnt[1] + cnt[2]) / cnt[0] <= 1.02 * ref_rpp
+
+
+def _cam():
+    return Camera(Vec3(0, 0, 20.0), Vec3(0, 0, 0), Vec3(0, 1, 0), 40.0, 33 / 17)
+
+
+def test_empty_scene():
+    scene = Scene()
+    W, H = 33, 17
+    img = np.asarray(renderer.B200PathTracer().render(scene, _cam(), RenderSettings(W, H, 3, 4)))
+    assert img.shape == (H, W, 3) and (img == 32).all()          # ACES(0.1) * 255 -> 32, the reference's sky
+    _, u8 = renderer.B200TextureRaytracer(precision="f64").render_float(scene, _cam(), RenderSettings(W, H, 4, 4))
+    assert (u8 == 0).all()
+    obj, t, pid = renderer.primary_hits(scene, _cam(), W, H)
+    assert (pid == -1).all()
+
+
+@pytest.mark.parametrize("kind", ["sphere", "plane", "triangle"])
+def test_single_primitive_scene(kind):
+    """n_prims == 1: the LBVH root is a leaf."""
+    scene = Scene()
+    m = Material(Vec3(0.8, 0.3, 0.2), diffuse=0.7, specular=0.2)
+    if kind == "sphere":
+        scene.add_object(Sphere(Vec3(0.5, 0.2, 0), 3.0, m))
+    elif kind == "plane":
+        scene.add_object(Plane(Vec3(-4, -3, 0), Vec3(0, 0, 1), Vec3(8, 0, 0), Vec3(0, 6, 0), 8, 6, m))
+    else:
+        scene.add_object(Triangle(Vec3(-4, -3, 0), Vec3(4, -3, 1), Vec3(0, 4, -1), None, None, None, m))
+    scene.add_light_sample(Vec3(3, 6, 10))
+    cam = _cam()
+    W, H = 33, 17
+    pk = O.nb_pack(scene, cam)
+    ref_ids, ref_t = O.nb_primary_hits(pk, W, H)
+    _, t, pid = renderer.primary_hits(scene, cam, W, H, "numba", "f64")
+    assert np.array_equal(pid, ref_ids) and np.array_equal(t, ref_t) and (pid >= 0).any()
+    ref = O.nb_path_trace(pk, W, H, 5, 4, 0)
+    r = renderer.B200PathTracer(precision="f64", rng="reference", spp_per_wave=2)       # 5 spp in waves of 2, 2, 1
+    acc, cnt = r.render_accum(scene, cam, RenderSettings(W, H, 5, 4))
+    assert np.isclose(acc[..., :3], ref["sum"], rtol=1e-9, atol=1e-12).all(axis=2).mean() >= 0.99
+    assert cnt[0] == W * H * 5
+    img = renderer.B200PathTracer(precision="f32").render(scene, cam, RenderSettings(W, H, 4, 1))      # depth 1
+    assert img.size == (W, H)
+
+
+def test_no_lights_and_depth_one():
+    scene, cam = RS.make_scene(RS.local_api(), 13, n_lights=0)
+    pk = O.nb_pack(scene, cam)
+    W, H = 40, 30
+    for depth in (1, 5):
+        ref = O.nb_path_trace(pk, W, H, 4, depth, 2)
+        r = renderer.B200PathTracer(precision="f64", rng="reference")
+        r.frame_count = 2
+        acc, cnt = r.render_accum(scene, cam, RenderSettings(W, H, 4, depth))
+        assert np.isclose(acc[..., :3], ref["sum"], rtol=1e-9, atol=1e-12).all(axis=2).mean() >= 0.99
+        assert cnt[2] == 0                                           # no shadow rays without lights
+
+
+def test_more_than_64_primitives_walks_the_lbvh():
+    """Above the small-scene threshold the float32 path uses the LBVH for every ray; still the same image
+    statistics as the generic scan of the float64 oracle."""
+    scene, cam = RS.make_scene(RS.local_api(), 21, n_rect=6, n_sphere=10, n_tri=70, with_textures=True)
+    assert len(scene.objects) > 64
+    pk = O.nb_pack(scene, cam)
+    o, d = _rays(3000, 5)
+    ref_ids, ref = O.nb_scene_hit_rays(pk, o, d)
+    ids, rec = renderer.trace_rays(scene, o, d, "numba", "f64")
+    assert np.array_equal(ids, ref_ids) and np.array_equal(rec[ids >= 0], ref[ids >= 0][:, :9])
+    W, H, n = 48, 36, 256
+    oref = O.nb_path_trace(pk, W, H, n, 5)
+    acc, cnt = renderer.B200PathTracer(precision="f32", seed=2).render_accum(scene, cam, RenderSettings(W, H, n, 5))
+    m, m_ref = acc[..., :3] / n, oref["sum"] / n
+    assert abs(m.mean() - m_ref.mean()) / m_ref.mean() < 0.05
+    r64 = renderer.B200PathTracer(precision="f64", rng="reference")
+    acc64, _ = r64.render_accum(scene, cam, RenderSettings(W, H, 4, 5))
+    o4 = O.nb_path_trace(pk, W, H, 4, 5)
+    assert np.isclose(acc64[..., :3], o4["sum"], rtol=1e-9, atol=1e-12).all(axis=2).mean() >= 0.99
