@@ -122,8 +122,12 @@ class DeviceScene:
                 self.scan_host, self.occluder_hint_host = _small_scene_records(packed, occluder_hints)
                 if self.scan_host is not None:
                     blob.add("scan", self.scan_host)
-                    if self.occluder_hint_host is not None:
-                        blob.add("hint", self.occluder_hint_host)
+            elif (not scan_ok and precision == _lib.P_F32 and packed.semantics == 0 and occluder_hints
+                  and 0 < packed.n_rect <= 64 and packed.n_sphere <= 64 and 0 < packed.lights.shape[0] <= 4096):
+                from .packer import build_occluder_hints, rect_scan_records
+                self.occluder_hint_host = build_occluder_hints(packed, rect_scan_records(packed), generic=True)
+            if self.occluder_hint_host is not None:
+                blob.add("hint", self.occluder_hint_host)
             d = blob.upload(dev)
             self._blob, self.h2d_small = d["_blob"], blob.nbytes
             self.rect, self.sphere, self.tri, self.shade = d["rect"], d["sphere"], d["tri"], d["shade"]
@@ -167,9 +171,9 @@ class DeviceScene:
         if self.scan_host is not None:
             self.scan_prims = d["scan"]
             s.n_scan_prims, s.d_scan_prims = self.scan_host.shape[0] // 4, self.scan_prims.data_ptr()
-            if self.occluder_hint_host is not None:
-                self.occluder_hint = d["hint"]
-                s.d_occluder_hint = self.occluder_hint.data_ptr()
+        if self.occluder_hint_host is not None:
+            self.occluder_hint = d["hint"]
+            s.d_occluder_hint = self.occluder_hint.data_ptr()
         self.struct = s
 
     def ref(self):

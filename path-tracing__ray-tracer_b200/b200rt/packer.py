@@ -377,7 +377,20 @@ def build_scan_prims(p: PackedScene, pair_tol: float = 1e-5) -> np.ndarray:
     return out.reshape(-1, 4)
 
 
-def build_occluder_hints(p: PackedScene, scan: np.ndarray, n_points: int = 4096, seed: int = 0) -> np.ndarray:
+def rect_scan_records(p: PackedScene) -> np.ndarray:
+    """Planar records of the rectangles only (candidate occluders of scenes that walk the LBVH)."""
+    R = p.rect.reshape(-1, 4, 4)
+    out = np.zeros((p.n_rect, 4, 4), dtype=np.float32)
+    for i in range(p.n_rect):
+        anchor, n, uu, vv = R[i, 0, :3], R[i, 1, :3], R[i, 2, :3], R[i, 3, :3]
+        out[i, 0], out[i, 1], out[i, 2] = [*n, n @ anchor], [*uu, -(uu @ anchor)], [*vv, -(vv @ anchor)]
+        out[i, 3, 0], out[i, 3, 1] = R[i, 0, 3], R[i, 1, 3]
+        out[i, 3, 2:4] = np.array([i, 0], dtype=np.int32).view(np.float32)
+    return out.reshape(-1, 4)
+
+
+def build_occluder_hints(p: PackedScene, scan: np.ndarray, n_points: int = 4096, seed: int = 0,
+                         generic: bool = False) -> np.ndarray:
     """For every light sample, the scan record (code k) or sphere (code 64 + i) that blocks the most
     next-event shadow rays towards it -> int32 [n_lights] (-1: none).
 
@@ -386,6 +399,8 @@ def build_occluder_hints(p: PackedScene, scan: np.ndarray, n_points: int = 4096,
     Cornell box the light samples sit at y = 14 *below* the ceiling at y = 15 and NEE shadow rays run to
     t_max = 1e6 (``cuda_path_tracer.py:275-277``), so the ceiling blocks ~92 % of them.
     Estimated here from area-weighted random surface points, both sides of every surface.
+    ``generic=True``: ``scan`` holds ``rect_scan_records`` and the codes are 128 + packed id (rectangle i ->
+    128 + i, sphere i -> 128 + n_rect + i), for scenes that have no scan records.
     """
     rng = np.random.default_rng(seed)
     n_lights = p.lights.shape[0]
@@ -401,8 +416,9 @@ def build_occluder_hints(p: PackedScene, scan: np.ndarray, n_points: int = 4096,
     for i in range(p.n_sphere):
         area.append(("s", i, 4 * np.pi * S[i, 0, 3] ** 2))
     T = p.tri.reshape(-1, 3, 4)
-    for i in range(p.n_tri):
-        area.append(("t", i, 0.5 * np.linalg.norm(np.cross(T[i, 1, :3], T[i, 2, :3]))))
+    tri_ids = range(p.n_tri) if p.n_tri <= 2048 else rng.choice(p.n_tri, 2048, replace=False)
+    for i in tri_ids:
+        area.append(("t", int(i), 0.5 * np.linalg.norm(np.cross(T[i, 1, :3], T[i, 2, :3])) * (p.n_tri / len(tri_ids))))
     total = sum(a for _, _, a in area) or 1.0
     for kind, i, a in area:
         m = max(4, int(round(n_points * a / total)))
@@ -448,5 +464,8 @@ def build_occluder_hints(p: PackedScene, scan: np.ndarray, n_points: int = 4096,
             hit = (disc > 0) & (((-b - sq) > 1e-3) | ((-b + sq) > 1e-3))
             counts[64 + i] = int((ok & hit).sum())
         best = max(counts, key=counts.get)
-        hints[j] = best if counts[best] > 0 else -1
+        code = best
+        if generic:
+            code = 128 + (best if best < 64 else p.n_rect + (best - 64))
+        hints[j] = code if counts[best] > 0 else -1
     return hints

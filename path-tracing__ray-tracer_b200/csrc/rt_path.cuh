@@ -185,7 +185,7 @@ template <typename R> struct Segment {       // what one loop iteration of cuda_
 
 // One loop iteration of cuda_trace_path (:229-469) for one path: sky / texture / NEE shadow-ray
 // emission / Russian roulette / BSDF sampling.  thr and rng come in through g and are updated.
-template <typename R, typename Rng, bool FIRST>
+template <typename R, typename Rng, bool FIRST, bool GENERIC_HINT>
 __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueues<R> &Q, const float4 *s_scan,
                                               const Ray<R> &r, const Hit<R> &h, int slot, int bounce, int max_depth,
                                               Segment<R> &g) {
@@ -236,9 +236,12 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
                 // Occluder hint: test the primitive that blocks most shadow rays to this light sample first.
                 // If it blocks this ray the full occlusion query would also say "occluded", so the ray is
                 // answered here and never queued (exact, not an approximation).
-                if (want_shadow && s_scan) {
+                if (want_shadow && S.occl_hint && (GENERIC_HINT || s_scan)) {
                     Ray<float> sr; sr.o = s_o; sr.d = s_d;
-                    if (occluder_test(S, s_scan, __ldg(S.occl_hint + li), sr, 0.001f, 1000000.0f)) {
+                    const int code = __ldg(S.occl_hint + li);
+                    bool blocked = (GENERIC_HINT && !s_scan) ? occluder_test<true>(S, s_scan, code, sr, 0.001f, 1000000.0f)
+                                                             : occluder_test<false>(S, s_scan, code, sr, 0.001f, 1000000.0f);
+                    if (blocked) {
                         want_shadow = false;
                         g.culled = true;
                     }
@@ -357,7 +360,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             } else {
                 if constexpr (sizeof(R) == 4) scan_small<false>(S, s_top, r, 0.001f, 1000000.0f, h);
             }
-            shade_segment<R, Rng, MODE == 4>(S, Q, s_scan, r, h, slot, bounce, max_depth, g);
+            shade_segment<R, Rng, MODE == 4, MODE == 1 || MODE == 4>(S, Q, s_scan, r, h, slot, bounce, max_depth, g);
         }
         n_culled += g.culled ? 1u : 0u;
         int si, ni;

@@ -19,6 +19,9 @@ namespace b2rt {
 #ifndef B2RT_BOUNCE_MIN_BLOCKS
 #define B2RT_BOUNCE_MIN_BLOCKS 4      // resident CTAs/SM requested for the float32 planar-scan bounce kernel (64 regs)
 #endif
+#ifndef B2RT_WHILE_WHILE
+#define B2RT_WHILE_WHILE 0            // LBVH walk style (see traverse); measured per round in profiles/
+#endif
 #ifndef B2RT_BVH_MIN_BLOCKS
 #define B2RT_BVH_MIN_BLOCKS 4         // ... for the float32 LBVH-walk bounce kernels (measured 6729 vs 6600 Mpaths/s with 3)
 #endif
@@ -57,7 +60,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.scan_incoherent = s->scan_incoherent;
     d.n_scan = s->precision == B2RT_PRECISION_F32 ? s->n_scan_prims : 0;
     d.scan = reinterpret_cast<const float4 *>(s->d_scan_prims);
-    d.occl_hint = d.n_scan > 0 ? s->d_occluder_hint : nullptr;
+    d.occl_hint = s->precision == B2RT_PRECISION_F32 ? s->d_occluder_hint : nullptr;
     return d;
 }
 
@@ -228,6 +231,50 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
     best.t = t_max; best.prim = -1; best.a = R(0); best.b = R(0);
     if (S.n_prims == 0) return false;
     V3<R> id = {rcp_(r.d.x), rcp_(r.d.y), rcp_(r.d.z)};
+#if B2RT_WHILE_WHILE
+    // "while-while" walk: every lane first descends through internal nodes until it holds a leaf, then the
+    // leaves are intersected together.
+    constexpr int kDone = (int)0x80000000;                       // sentinel below every leaf reference
+    int stack[kStackDepth];
+    stack[0] = kDone;
+    int sp = 1;
+    int ref = S.root;
+    while (ref != kDone) {
+        while (ref >= 0) {
+            float4 n0, n1, n2, n3;
+            if (ref < S.n_top) {
+                const float4 *p = s_top + 4 * ref;
+                n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+            } else {
+                const float4 *p = S.nodes + 4 * (size_t)(ref - S.n_top);
+                n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
+            }
+            R tl, tr;
+            bool hl = slab<R>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, r.o, id, t_min, best.t, tl);
+            bool hr = slab<R>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, r.o, id, t_min, best.t, tr);
+            int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+            if (hl && hr) {
+                bool swap = tr < tl;
+                stack[sp++] = swap ? cl : cr;
+                ref = swap ? cr : cl;
+            } else if (hl) {
+                ref = cl;
+            } else if (hr) {
+                ref = cr;
+            } else {
+                ref = stack[--sp];
+            }
+        }
+        while (ref < 0 && ref != kDone) {
+            test_prim<R, CpuSem>(S, ~ref, r, t_min, best);
+            if (AnyHit && best.prim >= 0) return true;
+            ref = stack[--sp];
+        }
+    }
+    return best.prim >= 0;
+#else
+    // one node-or-leaf step per iteration; boxes are tested against the closed range [t_min, best.t]
+    // (ties, and CPU-semantics rectangles that accept t == t_far)
     int stack[kStackDepth];
     int sp = 0;
     int ref = S.root;
@@ -242,7 +289,6 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
                 n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
             }
             R tl, tr;
-            // CPU semantics accept t == t_far on a rectangle, so boxes are tested against the closed range
             bool hl = slab<R>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, r.o, id, t_min, best.t, tl);
             bool hr = slab<R>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, r.o, id, t_min, best.t, tr);
             int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
@@ -266,6 +312,7 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
         }
     }
     return best.prim >= 0;
+#endif
 }
 
 // brute-force scan in packed order (validation path; equals cuda_scene_hit's loop structure)
@@ -284,10 +331,19 @@ __device__ __forceinline__ bool scan_all(const SceneDev &S, const Ray<R> &r, R t
 // inside the loop), and a parallelogram record covers two triangles: ~40 instructions per record instead
 // of ~65 per triangle for the generic Moeller-Trumbore test.  Same result contract as traverse():
 // closest t, ties to the lowest packed id.
-// Occluder codes (shadow-ray cache): k in [0, n_scan) = planar record k, 64 + i = sphere i.
+// Occluder-hint codes: k in [0, n_scan) = planar scan record k, 64 + i = sphere i, 128 + p = packed primitive p
+// tested with the generic per-type test (scenes without scan records).
+template <bool GENERIC>
 __device__ __forceinline__ bool occluder_test(const SceneDev &S, const float4 *sp, int code, const Ray<float> &r,
                                               float t_min, float t_max) {
     if (code < 0) return false;
+    if (GENERIC) {
+        if (code < 128) return false;
+        Hit<float> h; h.t = t_max; h.prim = -1; h.a = 0.f; h.b = 0.f;
+        test_prim<float, false>(S, code - 128, r, t_min, h);
+        return h.prim >= 0;
+    }
+    if (sp == nullptr || code >= 128) return false;
     if (code >= 64) {
         float t;
         return hit_sphere<float>(S, code - 64, r, t_min, t_max, false, t);
