@@ -245,6 +245,9 @@ def main():
         r2 = renderer.B200PathTracer(precision="f32", rng="pcg", seed=0, device=dev)
         r2._ws = r._ws
         h2d = d2h = 0
+        r2._tex_cache.enabled = False
+        for _ in range(min(2, args.warmup)):                 # warm-up: pinned buffers, NCCL communicator
+            r2.render(scene, camera, settings)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):

@@ -113,10 +113,13 @@ class _B200Base(BaseRenderer):
 
     def _image_from_u8(self, u8: torch.Tensor, width: int, height: int):
         from PIL import Image
-        host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
-        host.copy_(u8, non_blocking=True)
+        n = u8.numel()
+        host = getattr(self, "_host_img", None)                # one pinned read-back buffer per renderer
+        if host is None or host.numel() < n:
+            host = self._host_img = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        host[:n].copy_(u8.reshape(-1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return Image.fromarray(host.numpy().reshape(height, width, 3), "RGB")
+        return Image.fromarray(host[:n].numpy().reshape(height, width, 3).copy(), "RGB")
 
 
 # ------------------------------------------------------------------------------------------ path tracer
@@ -169,7 +172,8 @@ class B200PathTracer(_B200Base):
                   accum=torch.zeros(W * H * 4, dtype=real, device=self.device),
                   accum_sq=torch.zeros(W * H * 4, dtype=real, device=self.device) if want_sumsq else None,
                   counters=torch.zeros(8, dtype=torch.int64, device=self.device),
-                  pixel_rng=torch.zeros(W * H, dtype=torch.int64, device=self.device),
+                  pixel_rng=(torch.zeros(W * H, dtype=torch.int64, device=self.device)
+                             if self.rng_mode == _lib.RNG_REFERENCE else None),
                   u8=torch.empty(W * H * 3, dtype=torch.uint8, device=self.device),
                   cam=_lib.dbl_array(ds.cam))
         return st
@@ -180,7 +184,8 @@ class B200PathTracer(_B200Base):
         _lib.check(self.lib.b2rt_render_path(
             st["ds"].ref(), st["cam"], st["W"], st["H"], st["spp_local"], st["offset"], st["wave"], st["depth"],
             self.rng_mode, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), self.flags, st["accum"].data_ptr(),
-            st["accum_sq"].data_ptr() if st["accum_sq"] is not None else None, st["pixel_rng"].data_ptr(),
+            st["accum_sq"].data_ptr() if st["accum_sq"] is not None else None,
+            st["pixel_rng"].data_ptr() if st["pixel_rng"] is not None else None,
             self._ws.data_ptr(), self._ws.numel(), st["counters"].data_ptr(), current_stream_ptr(self.device)),
             "b2rt_render_path")
 
