@@ -40,6 +40,7 @@ extern "C" {
 
 /* flags for b2rt_render_path */
 #define B2RT_PATH_UNFUSED 1
+#define B2RT_PATH_NO_RAY_SORT 2   /* keep queue order even if the scene asks for ray re-ordering */
 
 /* rng modes for b2rt_render_path */
 #define B2RT_RNG_PCG       0 /* counter-based: stream keyed by (pixel, global sample index, seed)        */
@@ -93,6 +94,11 @@ typedef struct b2rt_scene {
      * most shadow rays towards it, precomputed on the host (packer.build_occluder_hints).  The shade stage
      * tests this one primitive before queueing a shadow ray: a hit answers the occlusion query exactly. */
     const int32_t *d_occluder_hint;
+    /* > 0: scenes that walk the LBVH re-order every ray queue before it is traced (bounce >= 1): key =
+     * quantised direction (6 bits) | 24-bit Morton code of the origin quantised over [-extent, extent]^3,
+     * radix-sorted; the next bounce reads its rays through the permutation.  0 disables the sort. */
+    float ray_sort_extent;
+    int32_t reserved_;
 } b2rt_scene;
 
 const char *b2rt_last_error(void);

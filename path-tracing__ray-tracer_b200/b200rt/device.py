@@ -97,7 +97,7 @@ class DeviceScene:
 
     def __init__(self, packed: PackedScene, precision: int = _lib.P_F32, device=None,
                  top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
-                 scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True):
+                 scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True, ray_sort_min_prims: int = 4096):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.packed = packed
@@ -167,6 +167,7 @@ class DeviceScene:
         s.d_bvh_nodes, s.d_bvh_top = self.nodes.data_ptr(), self.top.data_ptr()
         s.n_bvh_top, s.bvh_root = self.n_top, self.root
         s.scan_incoherent = 1 if scan_ok else 0
+        s.ray_sort_extent = float(packed.max_abs_coordinate()) if (not scan_ok and packed.n_prims >= ray_sort_min_prims) else 0.0
         s.n_scan_prims, s.d_scan_prims, s.d_occluder_hint = 0, None, None
         if self.scan_host is not None:
             self.scan_prims = d["scan"]

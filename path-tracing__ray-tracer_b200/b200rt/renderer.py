@@ -137,9 +137,9 @@ class B200PathTracer(_B200Base):
 
     def __init__(self, precision="f32", rng="pcg", seed: int = 0, spp_per_wave: Optional[int] = None,
                  device=None, top_nodes: int = 512, wave_paths: int = 1 << 26, scan_max_prims: int = 64,
-                 fused: bool = True, occluder_hints: bool = True):
+                 fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True):
         super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints)
-        self.flags = 0 if fused else 1
+        self.flags = (0 if fused else 1) | (0 if sort_rays else 2)
         self.rng_mode = _RNG[rng]
         self.seed = int(seed)
         self.spp_per_wave = spp_per_wave

@@ -2,6 +2,8 @@
 #pragma once
 #include <type_traits>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "rt_api.h"
 #include "rt_path.cuh"
 #include "rt_whitted.cuh"
@@ -74,13 +76,20 @@ cudaError_t Api<R>::whitted_texture(const b2rt_scene *s, const double *cam, int 
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 template <typename R> struct PathLayout {
-    size_t stream_bytes, counts_off, total;
+    size_t stream_bytes, counts_off, sort_off, int_bytes, cub_bytes, total;
     static PathLayout make(int W, int H, int spp_per_wave, int max_depth) {
         PathLayout L;
         size_t n = (size_t)W * H * spp_per_wave;
         L.stream_bytes = align256(n * sizeof(real4<R>));
         L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
-        L.total = L.counts_off + align256(sizeof(unsigned long long) * ((size_t)max_depth + 3));
+        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * ((size_t)max_depth + 3));
+        // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
+        L.int_bytes = align256(n * sizeof(int));
+        L.cub_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, L.cub_bytes, (const unsigned *)nullptr, (unsigned *)nullptr,
+                                        (const int *)nullptr, (int *)nullptr, (int)n, 0, 30);
+        L.cub_bytes = align256(L.cub_bytes);
+        L.total = L.sort_off + 4 * L.int_bytes + L.cub_bytes;
         return L;
     }
 };
@@ -110,6 +119,12 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.unshadowed = counts + a.max_depth + 1;
     Q.culled = counts + a.max_depth + 2;
     size_t counts_bytes = sizeof(unsigned long long) * ((size_t)a.max_depth + 3);
+    const bool sort_rays = S.sort_inv > 0.f && !(a.flags & 2);
+    unsigned *keys = (unsigned *)(base + L.sort_off), *keys_sorted = (unsigned *)(base + L.sort_off + L.int_bytes);
+    int *iota = (int *)(base + L.sort_off + 2 * L.int_bytes), *perm = (int *)(base + L.sort_off + 3 * L.int_bytes);
+    void *cub_tmp = base + L.sort_off + 4 * L.int_bytes;
+    Q.keys = sort_rays ? keys : nullptr;
+    Q.perm = nullptr;
 
     const size_t smem = smem_top_bytes(S);
     const size_t smem_scan = (size_t)S.n_scan * 64;
@@ -136,9 +151,11 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     // camera rays are generated inside the first bounce kernel when the RNG is counter-based
     const bool fuse_primary = fused && std::is_same<Rng, PcgRng>::value;
     const int g_primary = persistent_grid((const void *)shade_kernel<R, PcgRng, 4>, T, smem_bvh);
+    if (sort_rays) iota_kernel<<<g_simple, T, 0, st>>>((int)((size_t)npix * wave), iota);
     for (int done = 0; done < a.spp_local; done += wave) {
         int k = a.spp_local - done < wave ? a.spp_local - done : wave;
         unsigned long long launches = 0;
+        Q.perm = nullptr;
         PrimaryArgs<R> PA;
         PA.cam = c; PA.W = W; PA.H = H; PA.spp_wave = k; PA.first_sample = a.sample_offset + done; PA.seed = a.seed;
         if ((e = cudaMemsetAsync(counts, 0, counts_bytes, st))) return e;
@@ -176,6 +193,24 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             prof_end(st);
             launches += 3;
             buf ^= 1;
+            Q.perm = nullptr;
+            if (sort_rays && b + 1 < a.max_depth) {
+                // the queue length lives on the device; CUB wants it on the host (one small sync per bounce,
+                // negligible next to a multi-millisecond LBVH bounce)
+                unsigned long long h_cnt = 0;
+                if ((e = cudaMemcpyAsync(&h_cnt, counts + b + 1, sizeof h_cnt, cudaMemcpyDeviceToHost, st))) return e;
+                if ((e = cudaStreamSynchronize(st))) return e;
+                int n_next = (int)(h_cnt & 0xffffffffULL);
+                if (n_next >= 65536) {
+                    prof_begin(kMisc, st);
+                    size_t tmp_bytes = L.cub_bytes;
+                    if ((e = cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, keys, keys_sorted, iota, perm, n_next, 0, 30, st)))
+                        return e;
+                    prof_end(st);
+                    ++launches;
+                    Q.perm = perm;
+                }
+            }
         }
         prof_begin(kAccumulate, st);
         accumulate_kernel<R><<<g_simple, T, 0, st>>>(npix, k, Q.L, (real4<R> *)a.accum, (real4<R> *)a.accum_sq);

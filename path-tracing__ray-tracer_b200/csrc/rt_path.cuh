@@ -67,7 +67,37 @@ template <typename R> struct PathQueues {
     unsigned long long *counts;            // [max_depth + 1]
     unsigned long long *unshadowed;        // [1]
     unsigned long long *culled;            // [1] shadow rays answered by the occluder hint (never queued)
+    unsigned *keys;                        // sort key of every ray appended to the next queue (or nullptr)
+    const int *perm;                       // permutation the current queue is read through (or nullptr)
 };
+
+// Ray-reordering key.  Layout 2 (default): 2 bits per direction component (6 bits) above a 24-bit Morton code of
+// the origin; layout 0: octant | 27-bit Morton; layout 1: Morton | octant.
+__device__ __forceinline__ unsigned spread9(unsigned v) {
+    v &= 0x1ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+template <typename R> __device__ __forceinline__ unsigned ray_sort_key(V3<R> o, V3<R> d, float inv) {
+    float fx = fminf(fmaxf(((float)o.x * inv + 0.5f) * 512.f, 0.f), 511.f);
+    float fy = fminf(fmaxf(((float)o.y * inv + 0.5f) * 512.f, 0.f), 511.f);
+    float fz = fminf(fmaxf(((float)o.z * inv + 0.5f) * 512.f, 0.f), 511.f);
+    unsigned m = (spread9((unsigned)fx) << 2) | (spread9((unsigned)fy) << 1) | spread9((unsigned)fz);
+    unsigned oct = (d.x < R(0) ? 4u : 0u) | (d.y < R(0) ? 2u : 0u) | (d.z < R(0) ? 1u : 0u);
+#if B2RT_SORT_KEY == 1
+    return (m << 3) | oct;
+#elif B2RT_SORT_KEY == 2
+    unsigned qx = (unsigned)fminf(fmaxf(((float)d.x + 1.f) * 2.f, 0.f), 3.f);
+    unsigned qy = (unsigned)fminf(fmaxf(((float)d.y + 1.f) * 2.f, 0.f), 3.f);
+    unsigned qz = (unsigned)fminf(fmaxf(((float)d.z + 1.f) * 2.f, 0.f), 3.f);
+    return (((qx << 4) | (qy << 2) | qz) << 24) | (m >> 3);
+#else
+    return (oct << 27) | m;
+#endif
+}
 template <typename R> __device__ __forceinline__ int ray_count(const PathQueues<R> &Q, int bounce) {
     return (int)(Q.counts[bounce] & 0xffffffffULL);
 }
@@ -343,7 +373,8 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                 r = camera_ray<R>(P.cam, (R(x) + rnd) / R(P.W), (R(y) + rnd) / R(P.H));
                 slot = i; g.rng = state; g.thr = {R(1), R(1), R(1)};
             } else {
-                real4<R> a = ld_stream(ro + i), b = ld_stream(rd + i), c = ld_stream(th + i);
+                const int j = Q.perm ? __ldg(Q.perm + i) : i;          // sorted order (LBVH scenes) or queue order
+                real4<R> a = ld_stream(ro + j), b = ld_stream(rd + j), c = ld_stream(th + j);
                 r.o = xyz<R>(a); r.d = xyz<R>(b);
                 slot = (int)unpack_u<R>(a.w);
                 g.rng = unpack_u<R>(b.w);
@@ -374,6 +405,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             st_stream(no + ni, Real4<R>::make(g.new_o.x, g.new_o.y, g.new_o.z, pack_int<R>((int64_t)slot)));
             st_stream(nd + ni, Real4<R>::make(g.new_d.x, g.new_d.y, g.new_d.z, pack_int<R>((int64_t)g.rng)));
             st_stream(nt + ni, Real4<R>::make(g.thr.x, g.thr.y, g.thr.z, pack_int<R>((int64_t)(bounce + 1))));
+            if ((MODE == 1 || MODE == 4) && Q.keys) Q.keys[ni] = ray_sort_key<R>(g.new_o, g.new_d, S.sort_inv);
         }
     }
     warp_flush(Q.culled, n_culled);
@@ -437,6 +469,10 @@ accumulate_kernel(int npix, int spp_wave, const real4<R> *__restrict__ L, real4<
             accum_sq[pix] = q;
         }
     }
+}
+
+static __global__ void iota_kernel(int n, int *out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
 }
 
 static __global__ void path_counters_kernel(const unsigned long long *counts, const unsigned long long *unshadowed,

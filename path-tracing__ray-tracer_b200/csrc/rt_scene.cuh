@@ -22,6 +22,9 @@ namespace b2rt {
 #ifndef B2RT_WHILE_WHILE
 #define B2RT_WHILE_WHILE 0            // LBVH walk style (see traverse); measured per round in profiles/
 #endif
+#ifndef B2RT_SORT_KEY
+#define B2RT_SORT_KEY 2               // ray re-ordering key layout (see ray_sort_key; measured on C4: 0: 624, 1: 586, 2: 656 Mpaths/s)
+#endif
 #ifndef B2RT_BVH_MIN_BLOCKS
 #define B2RT_BVH_MIN_BLOCKS 4         // ... for the float32 LBVH-walk bounce kernels (measured 6729 vs 6600 Mpaths/s with 3)
 #endif
@@ -42,6 +45,7 @@ struct SceneDev {
     int n_scan;
     const float4 *scan;
     const int *occl_hint;
+    float sort_inv;                    // 0.5 / ray_sort_extent, or 0 when ray sorting is off
 };
 
 inline SceneDev make_scene_dev(const b2rt_scene *s) {
@@ -61,6 +65,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.n_scan = s->precision == B2RT_PRECISION_F32 ? s->n_scan_prims : 0;
     d.scan = reinterpret_cast<const float4 *>(s->d_scan_prims);
     d.occl_hint = s->precision == B2RT_PRECISION_F32 ? s->d_occluder_hint : nullptr;
+    d.sort_inv = (s->ray_sort_extent > 0.f && !s->scan_incoherent) ? 0.5f / s->ray_sort_extent : 0.f;
     return d;
 }
 
