@@ -46,6 +46,11 @@ def reference_cwd(texture_root: str | None = None):
     os.chdir(texture_root or REF_ROOT)
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
+    for top in ("renderers", "core", "scene_builders"):          # a same-named foreign package must not shadow the reference
+        m = sys.modules.get(top)
+        if m is not None and not str(getattr(m, "__file__", "") or "").startswith(REF_ROOT):
+            for k in [k for k in sys.modules if k == top or k.startswith(top + ".")]:
+                del sys.modules[k]
     try:
         yield
     finally:

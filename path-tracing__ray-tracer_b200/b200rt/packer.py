@@ -48,6 +48,37 @@ class TriangleMesh:
         self.material = material
 
 
+def load_obj(path: str, material, scale: float = 1.0, translate=(0.0, 0.0, 0.0)) -> TriangleMesh:
+    """Minimal Wavefront OBJ reader (v / vt / f with fan triangulation) -> ``TriangleMesh``."""
+    verts, uvs, faces, face_uv = [], [], [], []
+    with open(path) as f:
+        for line in f:
+            p = line.split()
+            if not p:
+                continue
+            if p[0] == "v":
+                verts.append([float(x) for x in p[1:4]])
+            elif p[0] == "vt":
+                uvs.append([float(x) for x in p[1:3]])
+            elif p[0] == "f":
+                idx = [tok.split("/") for tok in p[1:]]
+                vi = [int(t[0]) - 1 if int(t[0]) > 0 else len(verts) + int(t[0]) for t in idx]
+                ti = [int(t[1]) - 1 if len(t) > 1 and t[1] else -1 for t in idx]
+                for k in range(1, len(vi) - 1):
+                    faces.append([vi[0], vi[k], vi[k + 1]])
+                    face_uv.append([ti[0], ti[k], ti[k + 1]])
+    V = np.asarray(verts, dtype=np.float64) * scale + np.asarray(translate, dtype=np.float64)
+    F = np.asarray(faces, dtype=np.int64)
+    mesh_uv = None
+    if uvs and all(t >= 0 for tri in face_uv for t in tri):
+        # per-corner uv: duplicate vertices so that uvs are per vertex
+        FU = np.asarray(face_uv, dtype=np.int64)
+        V = V[F.reshape(-1)]
+        mesh_uv = np.asarray(uvs, dtype=np.float64)[FU.reshape(-1)]
+        F = np.arange(F.size).reshape(-1, 3)
+    return TriangleMesh(V, F, material, mesh_uv)
+
+
 def kind_of(obj) -> str:
     if isinstance(obj, TriangleMesh):
         return "mesh"

@@ -18,12 +18,19 @@ from typing import Dict, List
 
 
 def _reference_plugin():
+    import sys
+    before = set(sys.modules)
     try:
         from renderers.base_renderer import BaseRenderer as B, RendererFactory as F  # type: ignore
         if hasattr(F, "register") and hasattr(F, "create"):
             return B, F
     except Exception:
         pass
+    # an unrelated top-level package that happens to be called ``renderers`` must not stay imported on our
+    # account: it would shadow a reference checkout put on sys.path later
+    for m in set(sys.modules) - before:
+        if m == "renderers" or m.startswith("renderers."):
+            sys.modules.pop(m, None)
     return None
 
 

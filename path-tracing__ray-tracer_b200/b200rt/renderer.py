@@ -137,9 +137,14 @@ class B200PathTracer(_B200Base):
 
     def __init__(self, precision="f32", rng="pcg", seed: int = 0, spp_per_wave: Optional[int] = None,
                  device=None, top_nodes: int = 512, wave_paths: int = 1 << 26, scan_max_prims: int = 64,
-                 fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True):
+                 fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True, progressive: bool = False):
         super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints)
         self.flags = (0 if fused else 1) | (0 if sort_rays else 2)
+        # progressive=True: successive render() calls with the same size ADD their samples (global sample
+        # indices continue where the last call stopped) instead of discarding the previous frame — the
+        # accumulation the reference's frame_count reseed hints at (cuda_path_tracer.py:28,739,809)
+        self.progressive = progressive
+        self._prog = None
         self.rng_mode = _RNG[rng]
         self.seed = int(seed)
         self.spp_per_wave = spp_per_wave
@@ -159,6 +164,10 @@ class B200PathTracer(_B200Base):
         W, H, spp, depth = settings.width, settings.height, settings.samples_per_pixel, settings.max_depth
         rank, world = dist.rank_world()
         spp_local, offset = dist.split_samples(spp, rank, world)
+        done = 0
+        if self.progressive and self._prog is not None and self._prog["size"] == (W, H):
+            done = self._prog["spp"]
+        offset += done                              # this call's samples follow the ones already accumulated
         wave = self.spp_per_wave or max(1, min(max(spp_local, 1), self.wave_paths // max(1, W * H)))
         wave = max(1, min(wave, max(spp_local, 1)))
         need = C.c_size_t(0)
@@ -176,11 +185,32 @@ class B200PathTracer(_B200Base):
                              if self.rng_mode == _lib.RNG_REFERENCE else None),
                   u8=torch.empty(W * H * 3, dtype=torch.uint8, device=self.device),
                   cam=_lib.dbl_array(ds.cam))
+        st["spp_done_before"] = done
         return st
+
+    def _fold_progressive(self, st: dict) -> None:
+        """progressive mode: add this call's (already reduced) sums to the running total and resolve that."""
+        if not self.progressive:
+            return
+        size = (st["W"], st["H"])
+        if self._prog is None or self._prog["size"] != size:
+            self._prog = dict(size=size, accum=torch.zeros_like(st["accum"]), spp=0)
+        self._prog["accum"] += st["accum"]
+        self._prog["spp"] += st["spp"]
+        st["accum"], st["spp"] = self._prog["accum"], self._prog["spp"]
+
+    def reset(self) -> None:
+        """Forget the progressive accumulation (the next render() starts a new image)."""
+        self._prog = None
 
     def accumulate(self, st: dict) -> None:
         """Adds this rank's samples to ``st['accum']`` (asynchronous on the current stream)."""
-        seed = self.frame_count if self.rng_mode == _lib.RNG_REFERENCE else self.seed + 0x9E3779B97F4A7C15 * self.frame_count
+        if self.rng_mode == _lib.RNG_REFERENCE:
+            seed = self.frame_count                 # the reference reseeds per frame (:28)
+        elif self.progressive:
+            seed = self.seed                        # calls are told apart by their global sample indices
+        else:
+            seed = self.seed + 0x9E3779B97F4A7C15 * self.frame_count
         _lib.check(self.lib.b2rt_render_path(
             st["ds"].ref(), st["cam"], st["W"], st["H"], st["spp_local"], st["offset"], st["wave"], st["depth"],
             self.rng_mode, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), self.flags, st["accum"].data_ptr(),
@@ -204,6 +234,7 @@ class B200PathTracer(_B200Base):
             dist.reduce_to_root(st["accum"])
             if want_sumsq:
                 dist.reduce_to_root(st["accum_sq"])
+            self._fold_progressive(st)
             torch.cuda.synchronize(self.device)
             self.frame_count += 1
             out = (st["accum"].reshape(st["H"], st["W"], 4).cpu().numpy(), st["counters"].cpu().numpy())
@@ -220,6 +251,7 @@ class B200PathTracer(_B200Base):
             self.accumulate(st)
             ev1.record()
             dist.reduce_to_root(st["accum"])
+            self._fold_progressive(st)
             rank, world = dist.rank_world()
             img = None
             if rank == 0:

@@ -203,3 +203,25 @@ def test_gloo_world2_reduce(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "root ok" in outs[0]
+
+
+def test_obj_loader(tmp_path):
+    from b200rt import packer
+    from b200rt.scene_api import Material, Scene, Vec3
+    p = tmp_path / "quad.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nf 1/1 2/2 3/3 4/4\n")
+    mesh = packer.load_obj(str(p), Material(Vec3(1, 1, 1)), scale=2.0, translate=(1, 0, 0))
+    assert mesh.faces.shape == (2, 3) and mesh.uvs.shape == (6, 2)
+    sc = Scene(); sc.objects.append(mesh)
+    pk = packer.pack_scene(sc, "numba")
+    assert pk.n_tri == 2
+    assert np.allclose(pk.tri.reshape(-1, 3, 4)[0, 0, :3], [1, 0, 0]) and np.allclose(pk.tri.reshape(-1, 3, 4)[0, 1, :3], [2, 0, 0])
+    rec = packer.build_scan_prims(pk).reshape(-1, 4, 4)
+    assert rec.shape[0] == 1 and (rec[0, 3, 2].view(np.int32) >> 28) == 2          # the two triangles pair into one parallelogram
+
+
+def test_cli_parser_matches_reference_flags():
+    import b200rt.cli as cli
+    src = open(cli.__file__).read()
+    for flag in ("--renderer", "--scene", "--width", "--height", "--samples", "--depth", "--output", "--path-samples"):
+        assert flag in src
