@@ -41,6 +41,8 @@ extern "C" {
 /* flags for b2rt_render_path */
 #define B2RT_PATH_UNFUSED 1
 #define B2RT_PATH_NO_RAY_SORT 2   /* keep queue order even if the scene asks for ray re-ordering */
+#define B2RT_PATH_PRIMARY_SCAN 4  /* small scenes: primary rays also use the scan/box records instead of walking the LBVH
+                                     (measured on the Cornell box: 9313 vs 9430 Mpaths/s, so the walk is the default) */
 
 /* rng modes for b2rt_render_path */
 #define B2RT_RNG_PCG       0 /* counter-based: stream keyed by (pixel, global sample index, seed)        */
@@ -98,6 +100,16 @@ typedef struct b2rt_scene {
      * quantised direction (6 bits) | 24-bit Morton code of the origin quantised over [-extent, extent]^3,
      * radix-sorted; the next bounce reads its rays through the permutation.  0 disables the sort. */
     float ray_sort_extent;
+    /* Box records (float32 small-scene scan, packer.group_scan_boxes): planar records that are faces of a common
+     * parallelepiped (the Cornell walls, a cube) are tested together with ONE three-slab test in the box's own
+     * coordinates.  d_scan_prims then holds n_scan_prims planar records — the first n_scan_loose belong to no
+     * box and are scanned one by one, the rest are box faces kept for (u, v) / triangle-id recovery and as
+     * occluder hints — followed by n_scan_boxes box records of 4 float4:
+     *   (m0.xyz, d0) (m1.xyz, d1) (m2.xyz, d2)   l_k = m_k.P + d_k in [-1, 1] inside the box
+     *   (bits(f0|f1<<8|f2<<16|f3<<24), bits(f4|f5<<8), -, -)   f[2k + (l_k == +1)] = planar record of that face, 255 = none
+     * With n_scan_boxes == 0 set n_scan_loose = n_scan_prims. */
+    int32_t n_scan_loose;
+    int32_t n_scan_boxes;
     int32_t reserved_;
 } b2rt_scene;
 

@@ -97,7 +97,8 @@ class DeviceScene:
 
     def __init__(self, packed: PackedScene, precision: int = _lib.P_F32, device=None,
                  top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
-                 scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True, ray_sort_min_prims: int = 4096):
+                 scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True, ray_sort_min_prims: int = 4096,
+                 scan_boxes: bool = True):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.packed = packed
@@ -119,9 +120,10 @@ class DeviceScene:
             self.scan_host = self.occluder_hint_host = None
             scan_ok = 0 < packed.n_prims <= scan_max_prims
             if scan_ok and precision == _lib.P_F32 and packed.semantics == 0:
-                self.scan_host, self.occluder_hint_host = _small_scene_records(packed, occluder_hints)
+                self.scan_host, self.occluder_hint_host, self.n_scan_loose, self.scan_boxes_host = \
+                    _small_scene_records(packed, occluder_hints, scan_boxes)
                 if self.scan_host is not None:
-                    blob.add("scan", self.scan_host)
+                    blob.add("scan", np.concatenate([self.scan_host, self.scan_boxes_host]))
             elif (not scan_ok and precision == _lib.P_F32 and packed.semantics == 0 and occluder_hints
                   and 0 < packed.n_rect <= 64 and packed.n_sphere <= 64 and 0 < packed.lights.shape[0] <= 4096):
                 from .packer import build_occluder_hints, rect_scan_records
@@ -172,6 +174,7 @@ class DeviceScene:
         if self.scan_host is not None:
             self.scan_prims = d["scan"]
             s.n_scan_prims, s.d_scan_prims = self.scan_host.shape[0] // 4, self.scan_prims.data_ptr()
+            s.n_scan_loose, s.n_scan_boxes = self.n_scan_loose, self.scan_boxes_host.shape[0] // 4
         if self.occluder_hint_host is not None:
             self.occluder_hint = d["hint"]
             s.d_occluder_hint = self.occluder_hint.data_ptr()
@@ -187,21 +190,26 @@ class DeviceScene:
 _small_cache: dict = {}
 
 
-def _small_scene_records(packed: PackedScene, want_hints: bool):
-    """Scan records + occluder hints, cached on the bytes of the packed geometry (pure functions of it)."""
+def _small_scene_records(packed: PackedScene, want_hints: bool, want_boxes: bool = True):
+    """Scan records (planar, loose count, boxes) + occluder hints, cached on the bytes of the packed geometry
+    (pure functions of it) -> (planar records, hints, n_loose, box records)."""
     import hashlib
-    from .packer import build_occluder_hints, build_scan_prims
+    from .packer import build_occluder_hints, build_scan_prims, group_scan_boxes
     h = hashlib.blake2b(digest_size=16)
     for a in (packed.rect, packed.sphere, packed.tri, packed.lights):
         h.update(np.ascontiguousarray(a).tobytes())
-    key = (h.hexdigest(), bool(want_hints))
+    key = (h.hexdigest(), bool(want_hints), bool(want_boxes))
     if key not in _small_cache:
-        rec = build_scan_prims(packed)
+        quads = []
+        rec = build_scan_prims(packed, quads_out=quads)
         if not (0 < rec.shape[0] // 4 <= 64):
-            _small_cache[key] = (None, None)
+            _small_cache[key] = (None, None, 0, None)
         else:
+            n_loose, boxes = rec.shape[0] // 4, np.zeros((0, 4), np.float32)
+            if want_boxes:
+                rec, n_loose, boxes = group_scan_boxes(rec, quads)
             hints = build_occluder_hints(packed, rec) if (want_hints and 0 < packed.lights.shape[0] <= 4096) else None
-            _small_cache[key] = (rec, hints)
+            _small_cache[key] = (rec, hints, n_loose, boxes)
         if len(_small_cache) > 64:
             _small_cache.pop(next(iter(_small_cache)))
     return _small_cache[key]

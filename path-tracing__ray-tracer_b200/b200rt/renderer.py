@@ -85,10 +85,11 @@ class _B200Base(BaseRenderer):
     semantics = "numba"
 
     def __init__(self, name: str, precision="f32", device=None, top_nodes: int = 512, scan_max_prims: int = 64,
-                 occluder_hints: bool = True):
+                 occluder_hints: bool = True, scan_boxes: bool = True):
         super().__init__(name)
         self.scan_max_prims = scan_max_prims
         self.occluder_hints = occluder_hints
+        self.scan_boxes = scan_boxes
         try:
             self.device = require_cuda(device)
             self.lib = _lib.load()
@@ -106,7 +107,7 @@ class _B200Base(BaseRenderer):
         reach = float(np.abs(cam[:3]).max())
         ds = DeviceScene(packed, self.precision, self.device, self.top_nodes, ray_origin_extent=reach,
                          textures_dev=dev_tex, scan_max_prims=self.scan_max_prims,
-                         occluder_hints=self.occluder_hints)
+                         occluder_hints=self.occluder_hints, scan_boxes=self.scan_boxes)
         ds.cam = cam
         ds.h2d_total = ds.h2d_bytes() + self._tex_cache.uploaded_bytes
         return ds
@@ -137,9 +138,10 @@ class B200PathTracer(_B200Base):
 
     def __init__(self, precision="f32", rng="pcg", seed: int = 0, spp_per_wave: Optional[int] = None,
                  device=None, top_nodes: int = 512, wave_paths: int = 1 << 26, scan_max_prims: int = 64,
-                 fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True, progressive: bool = False):
-        super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints)
-        self.flags = (0 if fused else 1) | (0 if sort_rays else 2)
+                 fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True, progressive: bool = False,
+                 scan_boxes: bool = True, primary_scan: bool = False):
+        super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints, scan_boxes)
+        self.flags = (0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_scan else 0)
         # progressive=True: successive render() calls with the same size ADD their samples (global sample
         # indices continue where the last call stopped) instead of discarding the previous frame — the
         # accumulation the reference's frame_count reseed hints at (cuda_path_tracer.py:28,739,809)
@@ -404,14 +406,14 @@ def primary_hits(scene, camera, width, height, semantics="numba", precision="f64
 
 
 def trace_rays(scene, origins, dirs, semantics="numba", precision="f64", t_min=0.001, t_max=1000000.0,
-               any_hit=False, use_bvh=True, device=None, top_nodes=512, packed=None):
+               any_hit=False, use_bvh=True, device=None, top_nodes=512, packed=None, scan_boxes=True):
     """Closest/any hit for explicit rays -> (packed ids [n], rec [n, 9]: t, point, normal, uv)."""
     lib = _lib.load()
     device = require_cuda(device)
     with torch.cuda.device(device):
         packed = packed or pack_scene(scene, semantics)
         ds = DeviceScene(packed, _PREC[precision], device, top_nodes,
-                         ray_origin_extent=float(np.abs(np.asarray(origins)).max()))
+                         ray_origin_extent=float(np.abs(np.asarray(origins)).max()), scan_boxes=scan_boxes)
         o = to_device(np.ascontiguousarray(origins, dtype=np.float64), device)
         d = to_device(np.ascontiguousarray(dirs, dtype=np.float64), device)
         n = int(o.numel() // 3)

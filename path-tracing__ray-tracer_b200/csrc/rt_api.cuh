@@ -41,7 +41,7 @@ cudaError_t Api<R>::trace_rays(const b2rt_scene *s, int n, const double *o, cons
     SceneDev S = make_scene_dev(s);
     int T = 128;
     if (n <= 0) return cudaSuccess;
-    const size_t sm = use_bvh == 2 ? (size_t)S.n_scan * 64 + 64 : smem_top_bytes(S);
+    const size_t sm = use_bvh == 2 ? smem_scan_bytes(S) + 64 : smem_top_bytes(S);
     if (S.semantics == B2RT_SEM_CPU)
         trace_rays_kernel<R, true><<<(n + T - 1) / T, T, sm, st>>>(S, n, o, d, R(t_min), R(t_max), any_hit, use_bvh, ids, rec);
     else
@@ -127,7 +127,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.perm = nullptr;
 
     const size_t smem = smem_top_bytes(S);
-    const size_t smem_scan = (size_t)S.n_scan * 64;
+    const size_t smem_scan = smem_scan_bytes(S);
     const size_t smem_shadow = S.scan_incoherent ? smem_scan : smem;
     const int T = 256;
     static int g_extend = 0, g_shade = 0, g_shadow = 0, g_simple = 0;
@@ -151,6 +151,9 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     // camera rays are generated inside the first bounce kernel when the RNG is counter-based
     const bool fuse_primary = fused && std::is_same<Rng, PcgRng>::value;
     const int g_primary = persistent_grid((const void *)shade_kernel<R, PcgRng, 4>, T, smem_bvh);
+    // small scenes: coherent primary rays walk the LBVH (measured faster) unless B2RT_PATH_PRIMARY_SCAN is set
+    const bool primary_scan = planar && S.scan_incoherent && (a.flags & 4);
+    const int g_primary_scan = planar ? persistent_grid((const void *)shade_kernel<R, PcgRng, 5>, T, smem_scan) : 0;
     if (sort_rays) iota_kernel<<<g_simple, T, 0, st>>>((int)((size_t)npix * wave), iota);
     for (int done = 0; done < a.spp_local; done += wave) {
         int k = a.spp_local - done < wave ? a.spp_local - done : wave;
@@ -170,7 +173,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             const bool scan = b > 0 && S.scan_incoherent;
             if (b == 0 && fuse_primary) {
                 prof_begin(kShade, st);
-                shade_kernel<R, PcgRng, 4><<<g_primary, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth, PA);
+                if (primary_scan) shade_kernel<R, PcgRng, 5><<<g_primary_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth, PA);
+                else shade_kernel<R, PcgRng, 4><<<g_primary, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth, PA);
                 prof_end(st);
                 launches -= 1;
             } else if (fused) {

@@ -339,22 +339,24 @@ template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fu
 // MODE 1/2/3: fused extend+shade — the closest hit is found in-register (1: LBVH walk, 2: warp-uniform scan of
 // all primitives with the generic tests, 3: the float32 planar scan records) and shaded at once, so the FP32-issue-bound intersection work overlaps the
 // latency-bound shading loads in one kernel and the hit stream (32 B/segment) never touches HBM.
+// MODE 5: bounce 0 of a small scene: camera ray generated in-register and intersected with the scan/box records.
 template <typename R, typename Rng, int MODE>
-__global__ void __launch_bounds__(256, sizeof(R) != 4 ? 1 : (MODE == 3 ? B2RT_BOUNCE_MIN_BLOCKS : B2RT_BVH_MIN_BLOCKS))
+__global__ void __launch_bounds__(256, sizeof(R) != 4 ? 1 : ((MODE == 3 || MODE == 5) ? B2RT_BOUNCE_MIN_BLOCKS : B2RT_BVH_MIN_BLOCKS))
 shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth, PrimaryArgs<R> P) {
+    constexpr bool PRIMARY = MODE == 4 || MODE == 5, WALK = MODE == 1 || MODE == 4, PLANAR = MODE == 3 || MODE == 5;
     extern __shared__ float4 s_top[];
-    if (MODE == 1 || MODE == 4) stage_top(S, s_top);
-    if (MODE == 3) stage_scan(S, s_top);         // s_top then holds the scan records
-    // scan records for the occluder cache: behind the BVH top copy in MODE 1, the records themselves in MODE 2
+    if (WALK) stage_top(S, s_top);
+    if (PLANAR) stage_scan(S, s_top);            // s_top then holds the scan records
+    // scan records for the occluder cache: behind the BVH top copy when walking, the records themselves otherwise
     const float4 *s_scan = nullptr;
     if (sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && S.occl_hint) {
-        if (MODE == 1 || MODE == 4) { stage_scan(S, s_top + 4 * S.n_top); s_scan = s_top + 4 * S.n_top; }
-        else if (MODE == 3) s_scan = s_top;
+        if (WALK) { stage_scan(S, s_top + 4 * S.n_top); s_scan = s_top + 4 * S.n_top; }
+        else if (PLANAR) s_scan = s_top;
     }
     const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
     real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
-    int n = MODE == 4 ? P.W * P.H * P.spp_wave : ray_count(Q, bounce);
-    if (MODE == 4 && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)n;   // for the ray statistics
+    int n = PRIMARY ? P.W * P.H * P.spp_wave : ray_count(Q, bounce);
+    if (PRIMARY && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)n;   // for the ray statistics
     int n_round = (n + 31) & ~31;                // whole warps iterate together (ballots in warp_append2)
     unsigned n_culled = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -364,7 +366,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         int slot = 0;
         if (valid) {
             Ray<R> r;
-            if (MODE == 4) {                     // cuda_path_trace_kernel's sample set-up (:35-41)
+            if (PRIMARY) {                       // cuda_path_trace_kernel's sample set-up (:35-41)
                 const int npix = P.W * P.H, pix = i % npix, s = i / npix;
                 const int x = pix % P.W, y = pix / P.W;
                 uint64_t state = PcgRng::seed((uint32_t)pix, (uint64_t)(P.first_sample + s), P.seed);
@@ -384,14 +386,14 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             if (MODE == 0) {
                 real4<R> hrec = ld_stream(Q.hit + i);
                 h.t = hrec.x; h.prim = (int)(long long)real_as_int(hrec.y); h.a = hrec.z; h.b = hrec.w;
-            } else if (MODE == 1 || MODE == 4) {
+            } else if (WALK) {
                 traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
             } else if (MODE == 2) {
                 scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
             } else {
                 if constexpr (sizeof(R) == 4) scan_small<false>(S, s_top, r, 0.001f, 1000000.0f, h);
             }
-            shade_segment<R, Rng, MODE == 4, MODE == 1 || MODE == 4>(S, Q, s_scan, r, h, slot, bounce, max_depth, g);
+            shade_segment<R, Rng, PRIMARY, WALK>(S, Q, s_scan, r, h, slot, bounce, max_depth, g);
         }
         n_culled += g.culled ? 1u : 0u;
         int si, ni;
@@ -405,7 +407,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             st_stream(no + ni, Real4<R>::make(g.new_o.x, g.new_o.y, g.new_o.z, pack_int<R>((int64_t)slot)));
             st_stream(nd + ni, Real4<R>::make(g.new_d.x, g.new_d.y, g.new_d.z, pack_int<R>((int64_t)g.rng)));
             st_stream(nt + ni, Real4<R>::make(g.thr.x, g.thr.y, g.thr.z, pack_int<R>((int64_t)(bounce + 1))));
-            if ((MODE == 1 || MODE == 4) && Q.keys) Q.keys[ni] = ray_sort_key<R>(g.new_o, g.new_d, S.sort_inv);
+            if (WALK && Q.keys) Q.keys[ni] = ray_sort_key<R>(g.new_o, g.new_d, S.sort_inv);
         }
     }
     warp_flush(Q.culled, n_culled);

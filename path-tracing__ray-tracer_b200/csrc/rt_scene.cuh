@@ -42,7 +42,7 @@ struct SceneDev {
     const float4 *nodes, *top;
     int n_top, root;
     int scan_incoherent;
-    int n_scan;
+    int n_scan, n_loose, n_box;        // planar scan records (loose ones first), box records behind them
     const float4 *scan;
     const int *occl_hint;
     float sort_inv;                    // 0.5 / ray_sort_extent, or 0 when ray sorting is off
@@ -63,6 +63,8 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.n_top = s->n_bvh_top; d.root = s->bvh_root;
     d.scan_incoherent = s->scan_incoherent;
     d.n_scan = s->precision == B2RT_PRECISION_F32 ? s->n_scan_prims : 0;
+    d.n_box = d.n_scan > 0 ? s->n_scan_boxes : 0;
+    d.n_loose = d.n_box > 0 ? s->n_scan_loose : d.n_scan;
     d.scan = reinterpret_cast<const float4 *>(s->d_scan_prims);
     d.occl_hint = s->precision == B2RT_PRECISION_F32 ? s->d_occluder_hint : nullptr;
     d.sort_inv = (s->ray_sort_extent > 0.f && !s->scan_incoherent) ? 0.5f / s->ray_sort_extent : 0.f;
@@ -365,37 +367,107 @@ __device__ __forceinline__ bool occluder_test(const SceneDev &S, const float4 *s
     return inside && fabsf(dn) > 1e-6f && t > t_min && t < t_max;
 }
 
+// Folds planar record k into the running closest hit (shared by the loose-record loop).
+template <bool AnyHit>
+__device__ __forceinline__ bool scan_planar(const float4 *sp, int k, float ox, float oy, float oz, float dx, float dy,
+                                            float dz, float t_min, Hit<float> &best) {
+    const float4 q0 = sp[4 * k], q1 = sp[4 * k + 1], q2 = sp[4 * k + 2], q3 = sp[4 * k + 3];
+    float dn = q0.x * dx + q0.y * dy + q0.z * dz;
+    float T = q0.w - (q0.x * ox + q0.y * oy + q0.z * oz);
+    float t = __fdividef(T, dn);
+    float px = fmaf(t, dx, ox), py = fmaf(t, dy, oy), pz = fmaf(t, dz, oz);
+    float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
+    float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
+    const int w = __float_as_int(q3.z), kind = w >> 28;          // warp-uniform
+    int id = w & 0x0fffffff;
+    bool inside = u >= 0.f && v >= 0.f;
+    float a = u, b = v;
+    if (kind == 1) inside = inside && (u + v <= 1.f);
+    else inside = inside && u <= q3.x && v <= q3.y;
+    if (kind >= 2) {
+        bool first = kind == 2 ? (u >= v) : (u > v);
+        id = first ? id : __float_as_int(q3.w);
+        a = first ? u - v : u;
+        b = first ? v : v - u;
+    }
+    bool ok = inside && fabsf(dn) > 1e-6f && t > t_min && (t < best.t || (t == best.t && id < best.prim));
+    if (ok) { best.t = t; best.prim = id; best.a = a; best.b = b; }
+    return ok;
+}
+
+// Box record j (see b2rt_scene.n_scan_boxes): three slabs in the box's own coordinates.  The candidate hit is the
+// first boundary crossing beyond t_min whose face exists; returns the planar record index of that face or -1.
+__device__ __forceinline__ int scan_box(const float4 *bx, int j, float ox, float oy, float oz, float dx, float dy,
+                                        float dz, float t_min, float t_far, float &t_out) {
+    const float4 q0 = bx[4 * j], q1 = bx[4 * j + 1], q2 = bx[4 * j + 2], q3 = bx[4 * j + 3];
+    const float lo0 = fmaf(q0.x, ox, fmaf(q0.y, oy, fmaf(q0.z, oz, q0.w)));
+    const float lo1 = fmaf(q1.x, ox, fmaf(q1.y, oy, fmaf(q1.z, oz, q1.w)));
+    const float lo2 = fmaf(q2.x, ox, fmaf(q2.y, oy, fmaf(q2.z, oz, q2.w)));
+    const float ld0 = fmaf(q0.x, dx, fmaf(q0.y, dy, q0.z * dz));
+    const float ld1 = fmaf(q1.x, dx, fmaf(q1.y, dy, q1.z * dz));
+    const float ld2 = fmaf(q2.x, dx, fmaf(q2.y, dy, q2.z * dz));
+    // a direction parallel to a slab gives +-inf crossings (outside: both the same infinity -> miss)
+    const float r0 = rcp_(ld0), r1 = rcp_(ld1), r2 = rcp_(ld2);
+    const float a0 = (-1.f - lo0) * r0, b0 = (1.f - lo0) * r0;
+    const float a1 = (-1.f - lo1) * r1, b1 = (1.f - lo1) * r1;
+    const float a2 = (-1.f - lo2) * r2, b2 = (1.f - lo2) * r2;
+    const float n0 = fminf(a0, b0), f0 = fmaxf(a0, b0);
+    const float n1 = fminf(a1, b1), f1 = fmaxf(a1, b1);
+    const float n2 = fminf(a2, b2), f2 = fmaxf(a2, b2);
+    const float te = fmaxf(fmaxf(n0, n1), n2), tx = fminf(fminf(f0, f1), f2);
+    // face slot = 2 * axis + (face at l = +1); entering through l = +1 when the local direction is negative
+    const int fe = te == n0 ? (ld0 < 0.f ? 1 : 0) : te == n1 ? (ld1 < 0.f ? 3 : 2) : (ld2 < 0.f ? 5 : 4);
+    const int fx = tx == f0 ? (ld0 > 0.f ? 1 : 0) : tx == f1 ? (ld1 > 0.f ? 3 : 2) : (ld2 > 0.f ? 5 : 4);
+    const unsigned w0 = __float_as_uint(q3.x), w1 = __float_as_uint(q3.y);
+    const int ce = (int)(__byte_perm(w0, w1, fe) & 0xffu), cx = (int)(__byte_perm(w0, w1, fx) & 0xffu);
+    const bool use_e = te > t_min && ce != 255;
+    const float t = use_e ? te : tx;
+    const int c = use_e ? ce : cx;
+    t_out = t;
+    return (te <= tx && t > t_min && t < t_far && c != 255) ? c : -1;
+}
+
+// (u, v) -> triangle id / barycentrics of the hit on planar record k at distance best.t (box faces)
+__device__ __forceinline__ void scan_resolve_face(const float4 *sp, int k, float ox, float oy, float oz, float dx,
+                                                  float dy, float dz, Hit<float> &best) {
+    const float4 q1 = sp[4 * k + 1], q2 = sp[4 * k + 2], q3 = sp[4 * k + 3];
+    const float t = best.t;
+    float px = fmaf(t, dx, ox), py = fmaf(t, dy, oy), pz = fmaf(t, dz, oz);
+    float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
+    float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
+    const int w = __float_as_int(q3.z), kind = w >> 28;
+    int id = w & 0x0fffffff;
+    if (kind >= 2) {
+        bool first = kind == 2 ? (u >= v) : (u > v);
+        id = first ? id : __float_as_int(q3.w);
+        float a = first ? u - v : u, b = first ? v : v - u;
+        u = a; v = b;
+    }
+    best.prim = id; best.a = u; best.b = v;
+}
+
 template <bool AnyHit>
 __device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, const Ray<float> &r, float t_min,
                                            float t_max, Hit<float> &best, int *code_out = nullptr) {
     best.t = t_max; best.prim = -1; best.a = 0.f; best.b = 0.f;
     const float ox = r.o.x, oy = r.o.y, oz = r.o.z, dx = r.d.x, dy = r.d.y, dz = r.d.z;
+    if (S.n_box > 0) {
+        const float4 *bx = sp + 4 * S.n_scan;
+        int face = -1;
+        for (int j = 0; j < S.n_box; ++j) {
+            float t;
+            int c = scan_box(bx, j, ox, oy, oz, dx, dy, dz, t_min, best.t, t);
+            if (c >= 0) {
+                best.t = t; face = c;
+                if (AnyHit) { best.prim = 0; if (code_out) *code_out = c; return true; }
+            }
+        }
+        if (face >= 0) scan_resolve_face(sp, face, ox, oy, oz, dx, dy, dz, best);
+    }
 #pragma unroll kScanUnroll
-    for (int k = 0; k < S.n_scan; ++k) {
-        const float4 q0 = sp[4 * k], q1 = sp[4 * k + 1], q2 = sp[4 * k + 2], q3 = sp[4 * k + 3];
-        float dn = q0.x * dx + q0.y * dy + q0.z * dz;
-        float T = q0.w - (q0.x * ox + q0.y * oy + q0.z * oz);
-        float t = __fdividef(T, dn);
-        float px = fmaf(t, dx, ox), py = fmaf(t, dy, oy), pz = fmaf(t, dz, oz);
-        float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
-        float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
-        const int w = __float_as_int(q3.z), kind = w >> 28;          // warp-uniform
-        int id = w & 0x0fffffff;
-        bool inside = u >= 0.f && v >= 0.f;
-        float a = u, b = v;
-        if (kind == 1) inside = inside && (u + v <= 1.f);
-        else inside = inside && u <= q3.x && v <= q3.y;
-        if (kind >= 2) {
-            bool first = kind == 2 ? (u >= v) : (u > v);
-            id = first ? id : __float_as_int(q3.w);
-            a = first ? u - v : u;
-            b = first ? v : v - u;
-        }
-        bool ok = inside && fabsf(dn) > 1e-6f && t > t_min && (t < best.t || (t == best.t && id < best.prim));
-        if (ok) {
-            best.t = t; best.prim = id; best.a = a; best.b = b;
-            if (AnyHit) { if (code_out) *code_out = k; return true; }
-        }
+    for (int k = 0; k < S.n_loose; ++k) {
+        bool ok = scan_planar<AnyHit>(sp, k, ox, oy, oz, dx, dy, dz, t_min, best);
+        if (AnyHit && ok) { if (code_out) *code_out = k; return true; }
     }
     for (int i = 0; i < S.n_sphere; ++i) {
         int prim = S.n_rect + i;
@@ -409,8 +481,10 @@ __device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, 
     return best.prim >= 0;
 }
 
+inline size_t smem_scan_bytes(const SceneDev &S) { return (size_t)(S.n_scan + S.n_box) * 64; }
+
 __device__ __forceinline__ void stage_scan(const SceneDev &S, float4 *s_scan) {
-    for (int i = threadIdx.x; i < 4 * S.n_scan; i += blockDim.x) s_scan[i] = __ldg(S.scan + i);
+    for (int i = threadIdx.x; i < 4 * (S.n_scan + S.n_box); i += blockDim.x) s_scan[i] = __ldg(S.scan + i);
     __syncthreads();
 }
 

@@ -225,3 +225,92 @@ def test_cli_parser_matches_reference_flags():
     src = open(cli.__file__).read()
     for flag in ("--renderer", "--scene", "--width", "--height", "--samples", "--depth", "--output", "--path-samples"):
         assert flag in src
+
+
+def _np_planar(rec, o, d, t_min=1e-3, t_max=1e6):
+    """numpy restatement of the planar scan-record test -> (t, record index)"""
+    best_t = np.full(o.shape[0], t_max); best_k = np.full(o.shape[0], -1)
+    kinds = rec[:, 3, 2].astype(np.float32).view(np.int32) >> 28
+    for k in range(rec.shape[0]):
+        q0, q1, q2, q3 = rec[k].astype(np.float64)
+        dn = d @ q0[:3]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = (q0[3] - o @ q0[:3]) / dn
+            X = o + t[:, None] * d
+            u, v = X @ q1[:3] + q1[3], X @ q2[:3] + q2[3]
+            inside = (u >= 0) & (v >= 0) & ((u + v <= 1) if kinds[k] == 1 else ((u <= q3[0]) & (v <= q3[1])))
+            ok = inside & (np.abs(dn) > 1e-6) & (t > t_min) & (t < best_t)
+        best_t[ok], best_k[ok] = t[ok], k
+    return best_t, best_k
+
+
+def _np_boxes(boxes, o, d, t_min=1e-3, t_max=1e6):
+    """numpy restatement of csrc/rt_scene.cuh:scan_box -> (t, planar record index of the face)"""
+    best_t = np.full(o.shape[0], t_max); best_k = np.full(o.shape[0], -1)
+    for b in range(boxes.shape[0]):
+        M, off = boxes[b, :3, :3].astype(np.float64), boxes[b, :3, 3].astype(np.float64)
+        w = boxes[b, 3, :2].view(np.uint32)
+        code = np.array([(int(w[0]) >> (8 * i)) & 255 for i in range(4)] + [int(w[1]) & 255, (int(w[1]) >> 8) & 255])
+        lo, ld = o @ M.T + off, d @ M.T
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ta, tb = (-1 - lo) / ld, (1 - lo) / ld
+        tn, tf = np.fmin(ta, tb), np.fmax(ta, tb)
+        ke, kx = np.argmax(tn, axis=1), np.argmin(tf, axis=1)
+        rows = np.arange(o.shape[0])
+        te, tx = tn[rows, ke], tf[rows, kx]
+        fe = 2 * ke + (ld[rows, ke] < 0)
+        fx = 2 * kx + (ld[rows, kx] > 0)
+        ce, cx = code[fe], code[fx]
+        use_e = (te > t_min) & (ce != 255)
+        t = np.where(use_e, te, tx); c = np.where(use_e, ce, cx)
+        ok = (te <= tx) & (t > t_min) & (t < best_t) & (c != 255)
+        best_t[ok], best_k[ok] = t[ok], c[ok]
+    return best_t, best_k
+
+
+def test_box_records_group_cornell_and_match_planar_scan(cornell):
+    """packer.group_scan_boxes: the Cornell walls (5 faces) and the two cubes (6 faces each) become three box
+    records, the canvas stays loose; the three-slab box test finds the same face and distance as the planar
+    records it replaces (numpy restatement of both device tests, float64)."""
+    from b200rt import packer
+    pk = packer.pack_scene(cornell[0], "numba")
+    quads = []
+    rec0 = packer.build_scan_prims(pk, quads_out=quads)
+    rec, n_loose, boxes = packer.group_scan_boxes(rec0, quads)
+    rec, boxes = rec.reshape(-1, 4, 4), boxes.reshape(-1, 4, 4)
+    assert rec.shape[0] == 18 and n_loose == 1 and boxes.shape[0] == 3
+    faces = sorted(int(c) for b in boxes for c in b[3, :2].view(np.uint8)[:6] if c != 255)
+    assert faces == list(range(1, 18))                     # every non-loose record is a face of exactly one box
+    assert sorted(map(bytes, rec)) == sorted(map(bytes, rec0.reshape(-1, 4, 4)))   # a permutation, nothing altered
+    rng = np.random.default_rng(5)
+    n = 100000
+    o = rng.uniform(-14.9, 14.9, size=(n, 3))
+    o[: n // 4] = np.array([0.0, 0.0, 40.0]) + rng.normal(size=(n // 4, 3))        # from outside, like the camera
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[: n // 4, 2] = -np.abs(d[: n // 4, 2])
+    tp, kp = _np_planar(rec[n_loose:], o, d)
+    tb, kb = _np_boxes(boxes, o, d)
+    kp = np.where(kp >= 0, kp + n_loose, -1)
+    assert ((kp >= 0) == (kb >= 0)).mean() > 0.9999
+    both = (kp >= 0) & (kb >= 0)
+    assert np.abs(tp[both] - tb[both]).max() < 1e-4
+    # same distance => same point; the label differs only on shared edges and on the coplanar overlapping faces
+    # (cube 1 top / cube 2 bottom at y = -9.4, cube 1 bottom / floor), reachable only from inside a cube
+    assert (kp[both] == kb[both]).mean() > 0.995
+    outside = np.arange(n) < n // 4
+    assert (kp[both & outside] == kb[both & outside]).mean() > 0.9995
+    assert (kp >= 0).mean() > 0.6
+
+
+def test_box_grouping_leaves_unrelated_quads_alone():
+    from b200rt import packer
+    from b200rt.scene_api import Material, Plane, Scene, Vec3
+    sc = Scene()
+    m = Material(Vec3(1, 1, 1))
+    sc.objects.append(Plane(Vec3(0, 0, 0), Vec3(0, 1, 0), Vec3(1, 0, 0), Vec3(0, 0, 1), 2.0, 2.0, m))
+    sc.objects.append(Plane(Vec3(0, 3, 0), Vec3(0, 1, 0), Vec3(1, 0, 0), Vec3(0, 0, 1), 2.0, 1.0, m))   # other size
+    pk = packer.pack_scene(sc, "numba")
+    quads = []
+    rec0 = packer.build_scan_prims(pk, quads_out=quads)
+    rec, n_loose, boxes = packer.group_scan_boxes(rec0, quads)
+    assert n_loose == 2 and boxes.shape[0] == 0 and np.array_equal(rec, rec0)
