@@ -106,11 +106,19 @@ typedef struct b2rt_scene {
      * box and are scanned one by one, the rest are box faces kept for (u, v) / triangle-id recovery and as
      * occluder hints — followed by n_scan_boxes box records of 4 float4:
      *   (m0.xyz, d0) (m1.xyz, d1) (m2.xyz, d2)   l_k = m_k.P + d_k in [-1, 1] inside the box
-     *   (bits(f0|f1<<8|f2<<16|f3<<24), bits(f4|f5<<8), -, -)   f[2k + (l_k == +1)] = planar record of that face, 255 = none
+     *   (bits(f0|f1<<8|f2<<16|f3<<24), bits(f4|f5<<8), -, -)   f[2k + (l_k == +1)] = planar record of that face, 255 = none;
+     *   the two upper bytes of the second word must be 0
      * With n_scan_boxes == 0 set n_scan_loose = n_scan_prims. */
     int32_t n_scan_loose;
     int32_t n_scan_boxes;
     int32_t reserved_;
+    /* Optional (small float32 scenes; NULL otherwise): float4[5*n_prims] per-primitive shading records, staged in
+     * shared memory by the bounce kernels (packer.build_surface_records) — one branch-free, one-hop record instead
+     * of the per-type branches and the prim -> material -> texture chain of dependent loads:
+     *   (n.xyz | sphere centre.xyz, 1/radius or 0) (color.rgb, diffuse) (specular, reflective, refractive, ior)
+     *   (u0, du_a, du_b, bits(texture id)) (v0, dv_a, dv_b, bits(flags))   uv = uv0 + a*d_a + b*d_b;
+     *   flags bit 0 = flip the normal to face the ray (triangles) */
+    const void *d_surface_records;
 } b2rt_scene;
 
 const char *b2rt_last_error(void);

@@ -98,7 +98,7 @@ class DeviceScene:
     def __init__(self, packed: PackedScene, precision: int = _lib.P_F32, device=None,
                  top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
                  scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True, ray_sort_min_prims: int = 4096,
-                 scan_boxes: bool = True):
+                 scan_boxes: bool = True, surface_records: bool = True):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.packed = packed
@@ -123,7 +123,10 @@ class DeviceScene:
                 self.scan_host, self.occluder_hint_host, self.n_scan_loose, self.scan_boxes_host = \
                     _small_scene_records(packed, occluder_hints, scan_boxes)
                 if self.scan_host is not None:
+                    from .packer import build_surface_records
                     blob.add("scan", np.concatenate([self.scan_host, self.scan_boxes_host]))
+                    if surface_records:
+                        blob.add("surf", build_surface_records(packed))
             elif (not scan_ok and precision == _lib.P_F32 and packed.semantics == 0 and occluder_hints
                   and 0 < packed.n_rect <= 64 and packed.n_sphere <= 64 and 0 < packed.lights.shape[0] <= 4096):
                 from .packer import build_occluder_hints, rect_scan_records
@@ -170,11 +173,14 @@ class DeviceScene:
         s.n_bvh_top, s.bvh_root = self.n_top, self.root
         s.scan_incoherent = 1 if scan_ok else 0
         s.ray_sort_extent = float(packed.max_abs_coordinate()) if (not scan_ok and packed.n_prims >= ray_sort_min_prims) else 0.0
-        s.n_scan_prims, s.d_scan_prims, s.d_occluder_hint = 0, None, None
+        s.n_scan_prims, s.d_scan_prims, s.d_occluder_hint, s.d_surface_records = 0, None, None, None
         if self.scan_host is not None:
             self.scan_prims = d["scan"]
             s.n_scan_prims, s.d_scan_prims = self.scan_host.shape[0] // 4, self.scan_prims.data_ptr()
             s.n_scan_loose, s.n_scan_boxes = self.n_scan_loose, self.scan_boxes_host.shape[0] // 4
+            if "surf" in d:
+                self.surface_records = d["surf"]
+                s.d_surface_records = self.surface_records.data_ptr()
         if self.occluder_hint_host is not None:
             self.occluder_hint = d["hint"]
             s.d_occluder_hint = self.occluder_hint.data_ptr()

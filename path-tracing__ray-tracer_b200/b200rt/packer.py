@@ -484,10 +484,52 @@ def group_scan_boxes(rec: np.ndarray, quads: list, tol: float = 1e-5):
         for slot, f in slots.items():
             code[slot] = new_index[f]
         assert max(new_index.values(), default=0) < 255
-        w = np.array([code[0] | code[1] << 8 | code[2] << 16 | code[3] << 24, code[4] | code[5] << 8 | 0xffff0000],
+        w = np.array([code[0] | code[1] << 8 | code[2] << 16 | code[3] << 24, code[4] | code[5] << 8],
                      dtype=np.uint32)
         out[b, 3, 0:2] = w.view(np.float32)
     return rec[order].reshape(-1, 4), len(loose), out.reshape(-1, 4)
+
+
+def build_surface_records(p: PackedScene) -> np.ndarray:
+    """Per-primitive shading records for small scenes (``b2rt_scene.d_surface_records``): float32 [5*n_prims, 4].
+
+    Everything ``cuda_scene_hit`` returns beside t (normal, uv, material; ``cuda_path_tracer.py:568-574,616-631,
+    706-728``) in ONE branch-free, one-hop record per primitive, staged in shared memory — instead of the per-type
+    branches and the prim -> material -> texture chain of dependent global loads of the generic streams:
+        (n.xyz | sphere centre.xyz, 1/radius or 0)  (color.rgb, diffuse)  (specular, reflective, refractive, ior)
+        (u0, du_a, du_b, bits(texture id))  (v0, dv_a, dv_b, bits(flags))     uv = uv0 + a * d_a + b * d_b
+    a, b = the hit's rectangle coordinates / triangle barycentrics; flags bit 0: flip the normal to face the ray
+    (triangles, ``dot(n, d) > 0``).  Rectangles: u = a / u_len, v = b / v_len; triangles: w uv0 + a uv1 + b uv2.
+    """
+    n = p.n_prims
+    out = np.zeros((n, 5, 4), dtype=np.float32)
+    R, S = p.rect.reshape(-1, 4, 4), p.sphere.reshape(-1, 2, 4)
+    SH = p.shade.reshape(-1, 3, 4)
+    flags = np.zeros(n, dtype=np.int32)
+    for i in range(p.n_rect):
+        out[i, 0, :3] = R[i, 1, :3]
+        out[i, 3, 1] = 1.0 / R[i, 0, 3]
+        out[i, 4, 2] = 1.0 / R[i, 1, 3]
+    for i in range(p.n_sphere):
+        k = p.n_rect + i
+        out[k, 0, :3] = S[i, 0, :3]
+        out[k, 0, 3] = 1.0 / S[i, 0, 3]
+    base = p.n_rect + p.n_sphere
+    for i in range(p.n_tri):
+        k = base + i
+        out[k, 0, :3] = SH[k, 0, :3]
+        flags[k] = 1
+        if SH[k, 2, 2] != 0:
+            uv0, uv1, uv2 = SH[k, 1, 0:2], SH[k, 1, 2:4], SH[k, 2, 0:2]
+            out[k, 3, :3] = (uv0[0], uv1[0] - uv0[0], uv2[0] - uv0[0])
+            out[k, 4, :3] = (uv0[1], uv1[1] - uv0[1], uv2[1] - uv0[1])
+    M = p.mat.reshape(-1, 2, 4)
+    for k in range(n):
+        m = int(p.prim_mat[k])
+        out[k, 1], out[k, 2] = M[m, 0], M[m, 1]
+    out[:, 3, 3] = p.mat_tex[p.prim_mat[:n]].astype(np.int32).view(np.float32) if n else 0
+    out[:, 4, 3] = flags.view(np.float32)
+    return out.reshape(-1, 4)
 
 
 def rect_scan_records(p: PackedScene) -> np.ndarray:

@@ -85,8 +85,9 @@ class _B200Base(BaseRenderer):
     semantics = "numba"
 
     def __init__(self, name: str, precision="f32", device=None, top_nodes: int = 512, scan_max_prims: int = 64,
-                 occluder_hints: bool = True, scan_boxes: bool = True):
+                 occluder_hints: bool = True, scan_boxes: bool = True, surface_records: bool = True):
         super().__init__(name)
+        self.surface_records = surface_records
         self.scan_max_prims = scan_max_prims
         self.occluder_hints = occluder_hints
         self.scan_boxes = scan_boxes
@@ -107,7 +108,8 @@ class _B200Base(BaseRenderer):
         reach = float(np.abs(cam[:3]).max())
         ds = DeviceScene(packed, self.precision, self.device, self.top_nodes, ray_origin_extent=reach,
                          textures_dev=dev_tex, scan_max_prims=self.scan_max_prims,
-                         occluder_hints=self.occluder_hints, scan_boxes=self.scan_boxes)
+                         occluder_hints=self.occluder_hints, scan_boxes=self.scan_boxes,
+                         surface_records=self.surface_records)
         ds.cam = cam
         ds.h2d_total = ds.h2d_bytes() + self._tex_cache.uploaded_bytes
         return ds
@@ -139,8 +141,9 @@ class B200PathTracer(_B200Base):
     def __init__(self, precision="f32", rng="pcg", seed: int = 0, spp_per_wave: Optional[int] = None,
                  device=None, top_nodes: int = 512, wave_paths: int = 1 << 26, scan_max_prims: int = 64,
                  fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True, progressive: bool = False,
-                 scan_boxes: bool = True, primary_scan: bool = False):
-        super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints, scan_boxes)
+                 scan_boxes: bool = True, primary_scan: bool = False, surface_records: bool = True):
+        super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints, scan_boxes,
+                         surface_records)
         self.flags = (0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_scan else 0)
         # progressive=True: successive render() calls with the same size ADD their samples (global sample
         # indices continue where the last call stopped) instead of discarding the previous frame — the

@@ -127,17 +127,19 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.perm = nullptr;
 
     const size_t smem = smem_top_bytes(S);
-    const size_t smem_scan = smem_scan_bytes(S);
-    const size_t smem_shadow = S.scan_incoherent ? smem_scan : smem;
+    const size_t smem_scan_only = smem_scan_bytes(S);
+    const size_t smem_shadow = S.scan_incoherent ? smem_scan_only : smem;
+    const size_t smem_scan = smem_scan_only + smem_surf_bytes(S);           // bounce kernels also stage the surface records
     const int T = 256;
     static int g_extend = 0, g_shade = 0, g_shadow = 0, g_simple = 0;
     // persistent grids: resident CTAs per SM x SM count (a multiple of the 148 SMs)
     g_extend = persistent_grid((const void *)extend_kernel<R>, T, smem);
     g_shade = persistent_grid((const void *)shade_kernel<R, Rng, 0>, T, 0);
     const bool fused = !(a.flags & 1);
-    const size_t smem_bvh = smem + (S.scan_incoherent ? smem_scan : 0);
+    const size_t smem_bvh = smem;                                           // MODE 1 / 4: generic streams only
+    const size_t smem_bvh_small = smem + smem_scan;                         // MODE 6: + scan and surface records
     const int g_fuse_bvh = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem_bvh);
-    const bool planar = sizeof(R) == 4 && S.n_scan > 0;
+    const bool planar = sizeof(R) == 4 && S.n_scan > 0 && S.surf != nullptr;
     const int g_fuse_scan = planar ? persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_scan)
                                    : persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, 0);
     g_shadow = persistent_grid((const void *)shadow_kernel<R>, T, smem_shadow);
@@ -151,6 +153,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     // camera rays are generated inside the first bounce kernel when the RNG is counter-based
     const bool fuse_primary = fused && std::is_same<Rng, PcgRng>::value;
     const int g_primary = persistent_grid((const void *)shade_kernel<R, PcgRng, 4>, T, smem_bvh);
+    const int g_primary_small = planar ? persistent_grid((const void *)shade_kernel<R, PcgRng, 6>, T, smem_bvh_small) : 0;
     // small scenes: coherent primary rays walk the LBVH (measured faster) unless B2RT_PATH_PRIMARY_SCAN is set
     const bool primary_scan = planar && S.scan_incoherent && (a.flags & 4);
     const int g_primary_scan = planar ? persistent_grid((const void *)shade_kernel<R, PcgRng, 5>, T, smem_scan) : 0;
@@ -174,6 +177,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             if (b == 0 && fuse_primary) {
                 prof_begin(kShade, st);
                 if (primary_scan) shade_kernel<R, PcgRng, 5><<<g_primary_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth, PA);
+                else if (planar && S.scan_incoherent) shade_kernel<R, PcgRng, 6><<<g_primary_small, T, smem_bvh_small, st>>>(S, Q, buf, b, a.max_depth, PA);
                 else shade_kernel<R, PcgRng, 4><<<g_primary, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth, PA);
                 prof_end(st);
                 launches -= 1;

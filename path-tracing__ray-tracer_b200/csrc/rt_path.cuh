@@ -171,7 +171,21 @@ __device__ __forceinline__ V3<R> cos_hemisphere(V3<R> n, uint64_t &rng) {
     R r2 = Rng::template random<R>(rng); rng = Rng::advance(rng);
     R ct = sqrt_(r1), st = sqrt_(R(1) - r1);
     R sp, cp;
-    if constexpr (sizeof(R) == 4) sincospif(2.0f * r2, &sp, &cp);
+#ifndef B2RT_OPT_ONB
+#define B2RT_OPT_ONB 1
+#endif
+    if constexpr (sizeof(R) == 4 && B2RT_OPT_ONB) {
+        // float32 production: MUFU sin/cos on phi - pi in [-pi, pi) (abs error 2^-21; the azimuth only has to be
+        // uniform) and the branch-free orthonormal basis of Duff et al. 2017 instead of cross / normalise / cross:
+        // the same cosine-weighted distribution about n with ~45 fewer instructions
+        const float phi = fmaf(r2, 6.2831853071795865f, -3.14159265358979f);
+        sp = __sinf(phi); cp = __cosf(phi);
+        const float x = st * cp, y = st * sp, z = ct;
+        const float sg = copysignf(1.0f, n.z);
+        const float a = -rcp_approx(sg + n.z), b = n.x * n.y * a;
+        const V3<R> u = {1.0f + sg * n.x * n.x * a, sg * b, -sg * n.x}, v = {b, sg + n.y * n.y * a, -n.y};
+        return {x * u.x + y * v.x + z * n.x, x * u.y + y * v.y + z * n.y, x * u.z + y * v.z + z * n.z};
+    } else if constexpr (sizeof(R) == 4) sincospif(2.0f * r2, &sp, &cp);
     else { R phi = R(2.0) * R(3.141592653589793) * r2; sp = sin(phi); cp = cos(phi); }
     R x = st * cp, y = st * sp, z = ct;
     V3<R> t = abs_(n.z) > R(0.9) ? V3<R>{R(1), R(0), R(0)} : V3<R>{R(0), R(0), R(1)};
@@ -215,9 +229,9 @@ template <typename R> struct Segment {       // what one loop iteration of cuda_
 
 // One loop iteration of cuda_trace_path (:229-469) for one path: sky / texture / NEE shadow-ray
 // emission / Russian roulette / BSDF sampling.  thr and rng come in through g and are updated.
-template <typename R, typename Rng, bool FIRST, bool GENERIC_HINT>
+template <typename R, typename Rng, bool FIRST, bool GENERIC_HINT, bool SURF>
 __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueues<R> &Q, const float4 *s_scan,
-                                              const Ray<R> &r, const Hit<R> &h, int slot, int bounce, int max_depth,
+                                              const float4 *s_surf, const Ray<R> &r, const Hit<R> &h, int slot, int bounce, int max_depth,
                                               Segment<R> &g) {
     V3<R> &thr = g.thr, &new_o = g.new_o, &new_d = g.new_d, &s_o = g.s_o, &s_d = g.s_d, &s_c = g.s_c;
     uint64_t &rng = g.rng;
@@ -227,14 +241,17 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
         Q.L[slot] = Real4<R>::make(sky, sky, sky, R(0));
     }
     if (h.prim < 0) {                                                       // :234-239 sky
-        if (!FIRST) {
-            real4<R> l = Q.L[slot];
-            Q.L[slot] = Real4<R>::make(l.x + thr.x * R(0.1), l.y + thr.y * R(0.1), l.z + thr.z * R(0.1), l.w);
-        }
+        if (!FIRST) add_stream(Q.L + slot, thr.x * R(0.1), thr.y * R(0.1), thr.z * R(0.1));
     } else {
         Surface<R> sf;
-        make_surface<R, false>(S, r, h, sf);
-        V3<R> mc = base_color<R, false>(S, sf);
+        if constexpr (SURF && sizeof(R) == 4) make_surface_small(s_surf, r, h, sf);
+        else make_surface<R, false>(S, r, h, sf);
+        // the texel load is issued here and decoded after the light-sample geometry and the occluder test below,
+        // which do not depend on it: the L2 round trip overlaps ~100 instructions of independent work
+        const bool textured = sf.tex >= 0 && sf.tex < S.n_tex;
+        uint32_t texel = 0;
+        if (textured) texel = fetch_texel<R, false>(S, sf.tex, sf.u, sf.v);
+        V3<R> mc = sf.color;
         V3<R> po = sf.p + sf.n * R(0.001);
         if (S.n_lights > 0) {                                               // :265-304
             R nl = R(S.n_lights);
@@ -250,6 +267,20 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
             if (sf.refractive > R(0.5)) { li_ = R(4.0); lm = R(0.6); }
             else if (sf.reflective > R(0.7)) { li_ = R(2.5); lm = R(0.8); }
             else { li_ = R(2.0); lm = R(1.0); }
+            s_o = po; s_d = l;
+            g.light = li;
+            bool blocked = false;
+            if constexpr (sizeof(R) == 4) {
+                // Occluder hint: test the primitive that blocks most shadow rays to this light sample first.
+                // If it blocks this ray the full occlusion query would also say "occluded", so the ray is
+                // answered here and never queued (exact, not an approximation).
+                if (ct * sf.diffuse != 0.f && S.occl_hint && (GENERIC_HINT || s_scan)) {
+                    Ray<float> sr; sr.o = s_o; sr.d = s_d;
+                    const int code = __ldg(S.occl_hint + li);
+                    blocked = occluder_test<GENERIC_HINT>(S, s_scan, code, sr, 0.001f, 1000000.0f);
+                }
+            }
+            if (textured) mc = decode_texel<R>(texel);
             if constexpr (sizeof(R) == 4) {
                 R k = sf.diffuse * ct * li_ * lm * nl;
                 s_c = {thr.x * (mc.x * k), thr.y * (mc.y * k), thr.z * (mc.z * k)};
@@ -260,24 +291,8 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
             }
             // a shadow ray whose payload is exactly zero cannot change the image: not queued
             want_shadow = (s_c.x != R(0)) || (s_c.y != R(0)) || (s_c.z != R(0));
-            s_o = po; s_d = l;
-            g.light = li;
-            if constexpr (sizeof(R) == 4) {
-                // Occluder hint: test the primitive that blocks most shadow rays to this light sample first.
-                // If it blocks this ray the full occlusion query would also say "occluded", so the ray is
-                // answered here and never queued (exact, not an approximation).
-                if (want_shadow && S.occl_hint && (GENERIC_HINT || s_scan)) {
-                    Ray<float> sr; sr.o = s_o; sr.d = s_d;
-                    const int code = __ldg(S.occl_hint + li);
-                    bool blocked = (GENERIC_HINT && !s_scan) ? occluder_test<true>(S, s_scan, code, sr, 0.001f, 1000000.0f)
-                                                             : occluder_test<false>(S, s_scan, code, sr, 0.001f, 1000000.0f);
-                    if (blocked) {
-                        want_shadow = false;
-                        g.culled = true;
-                    }
-                }
-            }
-        }
+            if (want_shadow && blocked) { want_shadow = false; g.culled = true; }
+        } else if (textured) mc = decode_texel<R>(texel);
         bool go = true;
         if (bounce >= 3) {                                                  // :307-314
             R p = max_(R(0.1), R(0.299) * thr.x + R(0.587) * thr.y + R(0.114) * thr.z);
@@ -326,6 +341,9 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
     }
 }
 
+#ifndef B2RT_OPT_SURF
+#define B2RT_OPT_SURF 1
+#endif
 template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fused into the first bounce
     Cam<R> cam;
     int W, H, spp_wave;
@@ -340,19 +358,24 @@ template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fu
 // all primitives with the generic tests, 3: the float32 planar scan records) and shaded at once, so the FP32-issue-bound intersection work overlaps the
 // latency-bound shading loads in one kernel and the hit stream (32 B/segment) never touches HBM.
 // MODE 5: bounce 0 of a small scene: camera ray generated in-register and intersected with the scan/box records.
+// MODE 6: MODE 4 for small float32 scenes (surface records + scan-record occluder hints; MODE 4 itself then only
+// carries the generic streams).  Each variant compiles ONE shading flavour: the fused kernels sit close to the
+// instruction-cache cliff (measured twice: ~27.6 KB of SASS ran at 44 ms where ~26.6 KB ran at 24 ms).
 template <typename R, typename Rng, int MODE>
 __global__ void __launch_bounds__(256, sizeof(R) != 4 ? 1 : ((MODE == 3 || MODE == 5) ? B2RT_BOUNCE_MIN_BLOCKS : B2RT_BVH_MIN_BLOCKS))
 shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth, PrimaryArgs<R> P) {
-    constexpr bool PRIMARY = MODE == 4 || MODE == 5, WALK = MODE == 1 || MODE == 4, PLANAR = MODE == 3 || MODE == 5;
+    constexpr bool PRIMARY = MODE == 4 || MODE == 5 || MODE == 6, WALK = MODE == 1 || MODE == 4 || MODE == 6,
+                   PLANAR = MODE == 3 || MODE == 5, SURF = B2RT_OPT_SURF && sizeof(R) == 4 && (PLANAR || MODE == 6);
+    // shared memory: [BVH top levels (WALK)] [scan + box records] [surface records]
     extern __shared__ float4 s_top[];
-    if (WALK) stage_top(S, s_top);
-    if (PLANAR) stage_scan(S, s_top);            // s_top then holds the scan records
-    // scan records for the occluder cache: behind the BVH top copy when walking, the records themselves otherwise
-    const float4 *s_scan = nullptr;
-    if (sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && S.occl_hint) {
-        if (WALK) { stage_scan(S, s_top + 4 * S.n_top); s_scan = s_top + 4 * S.n_top; }
-        else if (PLANAR) s_scan = s_top;
+    float4 *cursor = s_top;
+    if (WALK) { stage_top(S, s_top); cursor += 4 * S.n_top; }
+    const float4 *s_scan = nullptr, *s_surf = nullptr;
+    // the scan records are what PLANAR modes intersect; walking modes keep them for the occluder hints
+    if (sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && (PLANAR || S.occl_hint)) {
+        stage_scan(S, cursor); s_scan = cursor; cursor += 4 * (S.n_scan + S.n_box);
     }
+    if (SURF) { stage_surf(S, cursor); s_surf = cursor; }
     const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
     real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
     int n = PRIMARY ? P.W * P.H * P.spp_wave : ray_count(Q, bounce);
@@ -381,6 +404,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                 slot = (int)unpack_u<R>(a.w);
                 g.rng = unpack_u<R>(b.w);
                 g.thr = xyz<R>(c);
+                prefetch_l2(Q.L + slot);         // a miss adds the sky term to L[slot]: DRAM round trip started now
             }
             Hit<R> h;
             if (MODE == 0) {
@@ -391,9 +415,10 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             } else if (MODE == 2) {
                 scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
             } else {
-                if constexpr (sizeof(R) == 4) scan_small<false>(S, s_top, r, 0.001f, 1000000.0f, h);
+                if constexpr (sizeof(R) == 4) scan_small<false>(S, s_scan, r, 0.001f, 1000000.0f, h);
             }
-            shade_segment<R, Rng, PRIMARY, WALK>(S, Q, s_scan, r, h, slot, bounce, max_depth, g);
+            shade_segment<R, Rng, PRIMARY, WALK && !(sizeof(R) == 4 && MODE == 6), SURF>(S, Q, (PLANAR && !S.occl_hint) ? nullptr : s_scan, s_surf,
+                                                                r, h, slot, bounce, max_depth, g);
         }
         n_culled += g.culled ? 1u : 0u;
         int si, ni;
@@ -429,6 +454,7 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
         if (i < n) {
             real4<R> a = ld_stream(Q.so + i), b = ld_stream(Q.sd + i);
             Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
+            prefetch_l2(Q.L + (int)unpack_u<R>(a.w));
             Hit<R> h;
             bool occluded;                                                          // :275-277 t_max = 1e6
             if (!S.scan_incoherent) occluded = traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);
@@ -439,8 +465,8 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
             lit = !occluded;
             if (lit) {
                 int slot = (int)unpack_u<R>(a.w);
-                real4<R> c = ld_stream(Q.sc + i), l = Q.L[slot];
-                Q.L[slot] = Real4<R>::make(l.x + c.x, l.y + c.y, l.z + c.z, l.w);
+                real4<R> c = ld_stream(Q.sc + i);
+                add_stream(Q.L + slot, c.x, c.y, c.z);
             }
         }
         n_lit += lit ? 1u : 0u;

@@ -14,7 +14,7 @@
 namespace b2rt {
 
 #ifndef B2RT_SCAN_UNROLL
-#define B2RT_SCAN_UNROLL 2
+#define B2RT_SCAN_UNROLL 1
 #endif
 #ifndef B2RT_BOUNCE_MIN_BLOCKS
 #define B2RT_BOUNCE_MIN_BLOCKS 4      // resident CTAs/SM requested for the float32 planar-scan bounce kernel (64 regs)
@@ -45,6 +45,7 @@ struct SceneDev {
     int n_scan, n_loose, n_box;        // planar scan records (loose ones first), box records behind them
     const float4 *scan;
     const int *occl_hint;
+    const float4 *surf;                // per-primitive shading records of small float32 scenes (or nullptr)
     float sort_inv;                    // 0.5 / ray_sort_extent, or 0 when ray sorting is off
 };
 
@@ -67,6 +68,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.n_loose = d.n_box > 0 ? s->n_scan_loose : d.n_scan;
     d.scan = reinterpret_cast<const float4 *>(s->d_scan_prims);
     d.occl_hint = s->precision == B2RT_PRECISION_F32 ? s->d_occluder_hint : nullptr;
+    d.surf = s->precision == B2RT_PRECISION_F32 ? reinterpret_cast<const float4 *>(s->d_surface_records) : nullptr;
     d.sort_inv = (s->ray_sort_extent > 0.f && !s->scan_incoherent) ? 0.5f / s->ray_sort_extent : 0.f;
     return d;
 }
@@ -397,29 +399,30 @@ __device__ __forceinline__ bool scan_planar(const float4 *sp, int k, float ox, f
 
 // Box record j (see b2rt_scene.n_scan_boxes): three slabs in the box's own coordinates.  The candidate hit is the
 // first boundary crossing beyond t_min whose face exists; returns the planar record index of that face or -1.
+// The face slot (2 * axis + (l == +1)) rides in the three low mantissa bits of each crossing distance, so the
+// min / max reductions that find t_enter / t_exit carry "which face" along for free (t moves by <= 7 ulp).
 __device__ __forceinline__ int scan_box(const float4 *bx, int j, float ox, float oy, float oz, float dx, float dy,
                                         float dz, float t_min, float t_far, float &t_out) {
     const float4 q0 = bx[4 * j], q1 = bx[4 * j + 1], q2 = bx[4 * j + 2], q3 = bx[4 * j + 3];
     const float lo0 = fmaf(q0.x, ox, fmaf(q0.y, oy, fmaf(q0.z, oz, q0.w)));
     const float lo1 = fmaf(q1.x, ox, fmaf(q1.y, oy, fmaf(q1.z, oz, q1.w)));
     const float lo2 = fmaf(q2.x, ox, fmaf(q2.y, oy, fmaf(q2.z, oz, q2.w)));
-    const float ld0 = fmaf(q0.x, dx, fmaf(q0.y, dy, q0.z * dz));
-    const float ld1 = fmaf(q1.x, dx, fmaf(q1.y, dy, q1.z * dz));
-    const float ld2 = fmaf(q2.x, dx, fmaf(q2.y, dy, q2.z * dz));
-    // a direction parallel to a slab gives +-inf crossings (outside: both the same infinity -> miss)
-    const float r0 = rcp_(ld0), r1 = rcp_(ld1), r2 = rcp_(ld2);
-    const float a0 = (-1.f - lo0) * r0, b0 = (1.f - lo0) * r0;
-    const float a1 = (-1.f - lo1) * r1, b1 = (1.f - lo1) * r1;
-    const float a2 = (-1.f - lo2) * r2, b2 = (1.f - lo2) * r2;
-    const float n0 = fminf(a0, b0), f0 = fmaxf(a0, b0);
-    const float n1 = fminf(a1, b1), f1 = fmaxf(a1, b1);
-    const float n2 = fminf(a2, b2), f2 = fmaxf(a2, b2);
-    const float te = fmaxf(fmaxf(n0, n1), n2), tx = fminf(fminf(f0, f1), f2);
-    // face slot = 2 * axis + (face at l = +1); entering through l = +1 when the local direction is negative
-    const int fe = te == n0 ? (ld0 < 0.f ? 1 : 0) : te == n1 ? (ld1 < 0.f ? 3 : 2) : (ld2 < 0.f ? 5 : 4);
-    const int fx = tx == f0 ? (ld0 > 0.f ? 1 : 0) : tx == f1 ? (ld1 > 0.f ? 3 : 2) : (ld2 > 0.f ? 5 : 4);
+    // + 1e-30: a direction parallel to a slab gives huge finite crossings (never inf: tagging inf would make NaN)
+    const float r0 = rcp_approx(fmaf(q0.x, dx, fmaf(q0.y, dy, fmaf(q0.z, dz, 1e-30f))));
+    const float r1 = rcp_approx(fmaf(q1.x, dx, fmaf(q1.y, dy, fmaf(q1.z, dz, 1e-30f))));
+    const float r2 = rcp_approx(fmaf(q2.x, dx, fmaf(q2.y, dy, fmaf(q2.z, dz, 1e-30f))));
+    auto tag = [](float t, unsigned slot) { return __uint_as_float((__float_as_uint(t) & 0xfffffff8u) | slot); };
+    // crossings of the faces l_k = -1 / +1: (-+1 - lo) * r as ONE fma each (single rounding: exact to an ulp even
+    // for a ray that starts on a face, where lo -> +-1 cancels)
+    const float a0 = tag(fmaf(-lo0, r0, -r0), 0u), b0 = tag(fmaf(-lo0, r0, r0), 1u);
+    const float a1 = tag(fmaf(-lo1, r1, -r1), 2u), b1 = tag(fmaf(-lo1, r1, r1), 3u);
+    const float a2 = tag(fmaf(-lo2, r2, -r2), 4u), b2 = tag(fmaf(-lo2, r2, r2), 5u);
+    const float te = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
+    const float tx = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
+    // bytes 6 and 7 of (w0, w1) are zero: selector nibbles 7 clear the upper bytes of the result
     const unsigned w0 = __float_as_uint(q3.x), w1 = __float_as_uint(q3.y);
-    const int ce = (int)(__byte_perm(w0, w1, fe) & 0xffu), cx = (int)(__byte_perm(w0, w1, fx) & 0xffu);
+    const int ce = (int)__byte_perm(w0, w1, (__float_as_uint(te) & 7u) | 0x7770u);
+    const int cx = (int)__byte_perm(w0, w1, (__float_as_uint(tx) & 7u) | 0x7770u);
     const bool use_e = te > t_min && ce != 255;
     const float t = use_e ? te : tx;
     const int c = use_e ? ce : cx;
@@ -469,19 +472,51 @@ __device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, 
         bool ok = scan_planar<AnyHit>(sp, k, ox, oy, oz, dx, dy, dz, t_min, best);
         if (AnyHit && ok) { if (code_out) *code_out = k; return true; }
     }
+#ifndef B2RT_OPT_SPH
+#define B2RT_OPT_SPH 1
+#endif
+    if (!B2RT_OPT_SPH) {
+        for (int i = 0; i < S.n_sphere; ++i) {
+            int prim = S.n_rect + i;
+            float t;
+            bool allow_eq = best.prim >= 0 && prim < best.prim;
+            if (hit_sphere<float>(S, i, r, t_min, best.t, allow_eq, t)) {
+                best.t = t; best.prim = prim; best.a = 0.f; best.b = 0.f;
+                if (AnyHit) { if (code_out) *code_out = 64 + i; return true; }
+            }
+        }
+        return best.prim >= 0;
+    }
+    // spheres: the cancellation-free form of hit_sphere with 1 / (d.d) hoisted out of the loop
+    const float ia = rcp_approx(dx * dx + dy * dy + dz * dz);
+    const float4 *sph = reinterpret_cast<const float4 *>(S.sphere);
     for (int i = 0; i < S.n_sphere; ++i) {
-        int prim = S.n_rect + i;
-        float t;
-        bool allow_eq = best.prim >= 0 && prim < best.prim;
-        if (hit_sphere<float>(S, i, r, t_min, best.t, allow_eq, t)) {
-            best.t = t; best.prim = prim; best.a = 0.f; best.b = 0.f;
-            if (AnyHit) { if (code_out) *code_out = 64 + i; return true; }
+        const float4 s0 = __ldg(sph + 2 * i);
+        const float cx = ox - s0.x, cy = oy - s0.y, cz = oz - s0.z;
+        const float b = (cx * dx + cy * dy + cz * dz) * ia;              // b / a
+        const float px = fmaf(-b, dx, cx), py = fmaf(-b, dy, cy), pz = fmaf(-b, dz, cz);
+        const float disc = fmaf(s0.w, s0.w, -(px * px + py * py + pz * pz));     // r^2 - |centre to line|^2
+        if (disc > 0.f) {
+            const float sq = sqrt_(disc * ia);
+            const float t1 = -b - sq, t2 = -b + sq;
+            const float t = t_min < t1 ? t1 : t2;
+            const int prim = S.n_rect + i;
+            if (t_min < t && (t < best.t || (t == best.t && prim < best.prim))) {
+                best.t = t; best.prim = prim; best.a = 0.f; best.b = 0.f;
+                if (AnyHit) { if (code_out) *code_out = 64 + i; return true; }
+            }
         }
     }
     return best.prim >= 0;
 }
 
 inline size_t smem_scan_bytes(const SceneDev &S) { return (size_t)(S.n_scan + S.n_box) * 64; }
+inline size_t smem_surf_bytes(const SceneDev &S) { return S.surf ? (size_t)S.n_prims * 80 : 0; }
+
+__device__ __forceinline__ void stage_surf(const SceneDev &S, float4 *s_surf) {
+    for (int i = threadIdx.x; i < 5 * S.n_prims; i += blockDim.x) s_surf[i] = __ldg(S.surf + i);
+    __syncthreads();
+}
 
 __device__ __forceinline__ void stage_scan(const SceneDev &S, float4 *s_scan) {
     for (int i = threadIdx.x; i < 4 * (S.n_scan + S.n_box); i += blockDim.x) s_scan[i] = __ldg(S.scan + i);
@@ -543,10 +578,36 @@ __device__ __forceinline__ void make_surface(const SceneDev &S, const Ray<R> &r,
     sf.tex = __ldg(S.mat_tex + m);
 }
 
+// make_surface from the shared-memory surface records (b2rt_scene.d_surface_records): no per-type branch, one hop
+__device__ __forceinline__ void make_surface_small(const float4 *s_surf, const Ray<float> &r, const Hit<float> &h,
+                                                   Surface<float> &sf) {
+    const float4 *q = s_surf + 5 * h.prim;
+    const float4 s0 = q[0], s1 = q[1], s2 = q[2], s3 = q[3], s4 = q[4];
+    sf.p = r.o + r.d * h.t;
+    const bool sph = s0.w != 0.f;
+    float nx = sph ? (sf.p.x - s0.x) * s0.w : s0.x, ny = sph ? (sf.p.y - s0.y) * s0.w : s0.y,
+          nz = sph ? (sf.p.z - s0.z) * s0.w : s0.z;
+    const bool flip = (__float_as_int(s4.w) & 1) && (nx * r.d.x + ny * r.d.y + nz * r.d.z > 0.f);
+    sf.n = flip ? V3<float>{-nx, -ny, -nz} : V3<float>{nx, ny, nz};
+    sf.u = fmaf(h.b, s3.z, fmaf(h.a, s3.y, s3.x));
+    sf.v = fmaf(h.b, s4.z, fmaf(h.a, s4.y, s4.x));
+    sf.color = {s1.x, s1.y, s1.z}; sf.diffuse = s1.w;
+    sf.specular = s2.x; sf.reflective = s2.y; sf.refractive = s2.z; sf.ior = s2.w;
+    sf.tex = __float_as_int(s3.w);
+}
+
 // nearest-texel fetch with V flip: cuda_sample_texture (cuda_path_tracer.py:473-493) /
 // Texture.sample (core/material.py:13-21).  RGBX8 texel -> one 32-bit load.
+template <typename R> __device__ __forceinline__ V3<R> decode_texel(uint32_t px) {
+    if constexpr (sizeof(R) == 4) {          // one multiply instead of an IEEE division per channel
+        const float k = 1.0f / 255.0f;
+        return V3<R>{R(px & 255u) * k, R((px >> 8) & 255u) * k, R((px >> 16) & 255u) * k};
+    }
+    return V3<R>{R(px & 255u) / R(255), R((px >> 8) & 255u) / R(255), R((px >> 16) & 255u) / R(255)};
+}
+
 template <typename R, bool CpuSem>
-__device__ __forceinline__ V3<R> sample_texture(const SceneDev &S, int tex, R u, R v) {
+__device__ __forceinline__ uint32_t fetch_texel(const SceneDev &S, int tex, R u, R v) {
     int4 info = __ldg(S.tex_info + tex);       // offset, w, h
     int w = info.y, h = info.z;
     int iu, iv;
@@ -561,8 +622,12 @@ __device__ __forceinline__ V3<R> sample_texture(const SceneDev &S, int tex, R u,
         iu = max(0, min(w - 1, iu));
         iv = max(0, min(h - 1, iv));
     }
-    uint32_t px = __ldg(S.texels + (size_t)info.x + (size_t)iv * w + iu);
-    return V3<R>{R(px & 255u) / R(255), R((px >> 8) & 255u) / R(255), R((px >> 16) & 255u) / R(255)};
+    return __ldg(S.texels + (size_t)info.x + (size_t)iv * w + iu);
+}
+
+template <typename R, bool CpuSem>
+__device__ __forceinline__ V3<R> sample_texture(const SceneDev &S, int tex, R u, R v) {
+    return decode_texel<R>(fetch_texel<R, CpuSem>(S, tex, u, v));
 }
 
 template <typename R, bool CpuSem>
