@@ -12,7 +12,7 @@ One JSON line on rank 0:
   value        Mpaths/s, inputs resident in HBM, CUDA-event time of K steps, max over ranks
   e2e          the same through the public renderer API: render(scene, camera, settings) -> PIL image
                (scene + texture H2D and image D2H inside the timed region)
-  roofline     dominant kernel (extend: LBVH closest hit), algorithmic bytes / measured launch time
+  roofline     dominant kernel (fused closest-hit + shade bounce kernel), algorithmic queue bytes / measured launch time
   fp32         useful FP32 work (1 070 flop/ray) against the FMA peak measured in-run
   cpu_baseline the oracle port (C, float64, reference algorithm) on the host cores, bounded sample
 --impl reference times that CPU implementation instead (all host threads, bounded sample per step).
@@ -39,7 +39,9 @@ WORKLOAD = "cornell_path_1920x1080_1024spp_depth8"
 FLOPS_PER_RAY = 1070.0          # reference-algorithm intersection cost per ray (measured)
 QUEUE_RECORD_BYTES = 48.0       # one ray-queue or shadow-queue record (3 float4 streams)
 STEP_BYTES_PER_PATH = 550.0     # whole-wavefront queue traffic per path
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None   # dram bytes read+written per launch of the dominant kernel (profiles/)
+# dram__bytes_read.sum + dram__bytes_write.sum of the fused bounce kernel, averaged over the 8 bounce launches of one
+# 32-spp wave at 1080p (ncu --set full, profiles/r1d_ncu_full_one_wave_32spp.csv: 13.09 GB per wave)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 13.090496e9 / 8
 
 
 def build_scene():
@@ -108,7 +110,7 @@ def cpu_baseline(scene, camera, budget_s: float = 15.0, threads: int | None = No
     t0 = time.perf_counter()
     O.nb_path_trace(pk, w, h, 2, DEPTH, 0, want_stats=False)
     rate = w * h * 2 / (time.perf_counter() - t0)
-    spp = int(max(4, min(256, budget_s * rate / (w * h))))
+    spp = int(max(4, min(4096, budget_s * rate / (w * h))))
     t0 = time.perf_counter()
     res = O.nb_path_trace(pk, w, h, spp, DEPTH, 0, want_stats=False)
     dt = time.perf_counter() - t0

@@ -154,8 +154,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     const bool fuse_primary = fused && std::is_same<Rng, PcgRng>::value;
     const int g_primary = persistent_grid((const void *)shade_kernel<R, PcgRng, 4>, T, smem_bvh);
     const int g_primary_small = planar ? persistent_grid((const void *)shade_kernel<R, PcgRng, 6>, T, smem_bvh_small) : 0;
-    // small scenes: coherent primary rays walk the LBVH (measured faster) unless B2RT_PATH_PRIMARY_SCAN is set
-    const bool primary_scan = planar && S.scan_incoherent && (a.flags & 4);
+    // small scenes: primary rays use the scan/box records too unless B2RT_PATH_PRIMARY_WALK asks for the LBVH walk
+    const bool primary_scan = planar && S.scan_incoherent && !(a.flags & 4);
     const int g_primary_scan = planar ? persistent_grid((const void *)shade_kernel<R, PcgRng, 5>, T, smem_scan) : 0;
     if (sort_rays) iota_kernel<<<g_simple, T, 0, st>>>((int)((size_t)npix * wave), iota);
     for (int done = 0; done < a.spp_local; done += wave) {

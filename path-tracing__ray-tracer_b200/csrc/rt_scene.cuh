@@ -369,17 +369,20 @@ __device__ __forceinline__ bool occluder_test(const SceneDev &S, const float4 *s
     return inside && fabsf(dn) > 1e-6f && t > t_min && t < t_max;
 }
 
-// Folds planar record k into the running closest hit (shared by the loose-record loop).
+// Folds planar record k into the running closest hit (the loose-record loop).  The distance test comes first and
+// branches: with box records most scenes keep only a few loose records and most rays miss each of them, so the
+// (u, v) work runs for the few lanes that are in range.
 template <bool AnyHit>
 __device__ __forceinline__ bool scan_planar(const float4 *sp, int k, float ox, float oy, float oz, float dx, float dy,
                                             float dz, float t_min, Hit<float> &best) {
-    const float4 q0 = sp[4 * k], q1 = sp[4 * k + 1], q2 = sp[4 * k + 2], q3 = sp[4 * k + 3];
-    float dn = q0.x * dx + q0.y * dy + q0.z * dz;
-    float T = q0.w - (q0.x * ox + q0.y * oy + q0.z * oz);
-    float t = __fdividef(T, dn);
-    float px = fmaf(t, dx, ox), py = fmaf(t, dy, oy), pz = fmaf(t, dz, oz);
-    float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
-    float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
+    const float4 q0 = sp[4 * k];
+    const float dn = q0.x * dx + q0.y * dy + q0.z * dz;
+    const float t = (q0.w - (q0.x * ox + q0.y * oy + q0.z * oz)) * rcp_approx(dn);
+    if (!(t > t_min && t <= best.t && fabsf(dn) > 1e-6f)) return false;
+    const float4 q1 = sp[4 * k + 1], q2 = sp[4 * k + 2], q3 = sp[4 * k + 3];
+    const float px = fmaf(t, dx, ox), py = fmaf(t, dy, oy), pz = fmaf(t, dz, oz);
+    const float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
+    const float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
     const int w = __float_as_int(q3.z), kind = w >> 28;          // warp-uniform
     int id = w & 0x0fffffff;
     bool inside = u >= 0.f && v >= 0.f;
@@ -387,12 +390,12 @@ __device__ __forceinline__ bool scan_planar(const float4 *sp, int k, float ox, f
     if (kind == 1) inside = inside && (u + v <= 1.f);
     else inside = inside && u <= q3.x && v <= q3.y;
     if (kind >= 2) {
-        bool first = kind == 2 ? (u >= v) : (u > v);
+        const bool first = kind == 2 ? (u >= v) : (u > v);
         id = first ? id : __float_as_int(q3.w);
         a = first ? u - v : u;
         b = first ? v : v - u;
     }
-    bool ok = inside && fabsf(dn) > 1e-6f && t > t_min && (t < best.t || (t == best.t && id < best.prim));
+    const bool ok = inside && (t < best.t || id < best.prim);
     if (ok) { best.t = t; best.prim = id; best.a = a; best.b = b; }
     return ok;
 }

@@ -8,12 +8,12 @@ from b200rt import _lib, renderer
 from b200rt.cornell import CustomSceneBuilder
 from b200rt.scene_api import RenderSettings
 
-kw = dict(spp=128, W=1920, H=1080, depth=8, wave_paths=1 << 24, scan=64, top=512, steps=2, precision="f32", fused=1, hints=1, boxes=1, pscan=0, surf=1)
+kw = dict(spp=128, W=1920, H=1080, depth=8, wave_paths=1 << 24, scan=64, top=512, steps=2, precision="f32", fused=1, hints=1, boxes=1, pwalk=0, surf=1)
 for a in sys.argv[1:]:
     k, v = a.split("="); kw[k] = type(kw[k])(v)
 random.seed(0); b = CustomSceneBuilder(texture_dir=False); scene = b.build_scene(); cam = b.create_camera(kw["W"] / kw["H"])
 lib = _lib.load()
-r = renderer.B200PathTracer(precision=kw["precision"], wave_paths=kw["wave_paths"], scan_max_prims=kw["scan"], top_nodes=kw["top"], fused=bool(kw["fused"]), occluder_hints=bool(kw["hints"]), scan_boxes=bool(kw["boxes"]), primary_scan=bool(kw["pscan"]), surface_records=bool(kw["surf"]))
+r = renderer.B200PathTracer(precision=kw["precision"], wave_paths=kw["wave_paths"], scan_max_prims=kw["scan"], top_nodes=kw["top"], fused=bool(kw["fused"]), occluder_hints=bool(kw["hints"]), scan_boxes=bool(kw["boxes"]), primary_walk=bool(kw["pwalk"]), surface_records=bool(kw["surf"]))
 st = r.prepare(scene, cam, RenderSettings(kw["W"], kw["H"], kw["spp"], kw["depth"]))
 r.accumulate(st); torch.cuda.synchronize()
 st["counters"].zero_(); lib.b2rt_profile_enable(1)
@@ -28,7 +28,7 @@ clocks = sampler.stop()
 tfl = C.c_double(0); lib.b2rt_fp32_peak(200000, C.byref(tfl), None)
 ms = (C.c_double * 8)(); nl = (C.c_int64 * 8)(); lib.b2rt_profile_read(ms, nl); lib.b2rt_profile_enable(0)
 cnt = st["counters"].cpu().numpy(); dt = e0.elapsed_time(e1) * 1e-3
-print({k: kw[k] for k in ("spp", "wave_paths", "scan", "top", "precision", "fused", "hints", "boxes", "pscan", "surf")}, "wave", st["wave"],
+print({k: kw[k] for k in ("spp", "wave_paths", "scan", "top", "precision", "fused", "hints", "boxes", "pwalk", "surf")}, "wave", st["wave"],
       "Mpaths/s %.1f  Mrays/s %.1f  rays/path %.3f" % (cnt[0] / dt / 1e6, (cnt[1] + cnt[2]) / dt / 1e6, (cnt[1] + cnt[2]) / cnt[0]),
       "clocks", clocks, "fp32 peak %.1f TF" % tfl.value,
       "ms/step: " + " ".join(f"{n}={ms[i] / kw['steps']:.1f}" for i, n in enumerate(["raygen", "extend", "shade", "shadow", "accum"])))
