@@ -44,6 +44,12 @@ extern "C" {
 #define B2RT_PATH_PRIMARY_WALK 4  /* small scenes: primary rays walk the LBVH instead of using the scan/box records
                                      (measured on the Cornell box: 22.3 vs 21.8 ms per 128 spp, so the records are the default) */
 
+#define B2RT_PATH_FUSED_WALK 8    /* large scenes: keep the per-ray LBVH walk fused into the bounce kernel for bounces >= 1
+                                     instead of the persistent walk kernel (dynamic ray fetch) + wavefront shade stage */
+
+#define B2RT_PATH_WALK_PRIMARY 32 /* large scenes: primary rays too go through raygen + the persistent walk kernel instead of
+                                     the fused first-bounce kernel (measured slightly slower: coherent rays need no re-fetch) */
+
 /* rng modes for b2rt_render_path */
 #define B2RT_RNG_PCG       0 /* counter-based: stream keyed by (pixel, global sample index, seed)        */
 #define B2RT_RNG_REFERENCE 1 /* the reference's int64 xorshift, per-pixel sequential (cuda_path_tracer.py:28,61-71) */

@@ -141,10 +141,11 @@ class B200PathTracer(_B200Base):
     def __init__(self, precision="f32", rng="pcg", seed: int = 0, spp_per_wave: Optional[int] = None,
                  device=None, top_nodes: int = 512, wave_paths: int = 1 << 26, scan_max_prims: int = 64,
                  fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True, progressive: bool = False,
-                 scan_boxes: bool = True, primary_walk: bool = False, surface_records: bool = True):
+                 scan_boxes: bool = True, primary_walk: bool = False, surface_records: bool = True,
+                 fused_walk: bool = False, walk_primary: bool = False):
         super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints, scan_boxes,
                          surface_records)
-        self.flags = (0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_walk else 0)
+        self.flags = (0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_walk else 0) | (8 if fused_walk else 0) | (32 if walk_primary else 0)
         # progressive=True: successive render() calls with the same size ADD their samples (global sample
         # indices continue where the last call stopped) instead of discarding the previous frame — the
         # accumulation the reference's frame_count reseed hints at (cuda_path_tracer.py:28,739,809)

@@ -82,7 +82,8 @@ template <typename R> struct PathLayout {
         size_t n = (size_t)W * H * spp_per_wave;
         L.stream_bytes = align256(n * sizeof(real4<R>));
         L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
-        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * ((size_t)max_depth + 3));
+        // per-bounce queue tails, unshadowed, culled + one ray-fetch counter per bounce (extend_walk_kernel)
+        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (2 * (size_t)max_depth + 4));
         // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
         L.int_bytes = align256(n * sizeof(int));
         L.cub_bytes = 0;
@@ -118,7 +119,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.counts = counts;
     Q.unshadowed = counts + a.max_depth + 1;
     Q.culled = counts + a.max_depth + 2;
-    size_t counts_bytes = sizeof(unsigned long long) * ((size_t)a.max_depth + 3);
+    size_t counts_bytes = sizeof(unsigned long long) * (2 * (size_t)a.max_depth + 4);
+    unsigned long long *fetch = counts + a.max_depth + 3;                   // [max_depth] dynamic-fetch cursors
     const bool sort_rays = S.sort_inv > 0.f && !(a.flags & 2);
     unsigned *keys = (unsigned *)(base + L.sort_off), *keys_sorted = (unsigned *)(base + L.sort_off + L.int_bytes);
     int *iota = (int *)(base + L.sort_off + 2 * L.int_bytes), *perm = (int *)(base + L.sort_off + 3 * L.int_bytes);
@@ -143,6 +145,9 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     const int g_fuse_scan = planar ? persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_scan)
                                    : persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, 0);
     g_shadow = persistent_grid((const void *)shadow_kernel<R>, T, smem_shadow);
+    // large scenes: incoherent bounces run the persistent walk kernel + the wavefront shade stage
+    const bool walk_kernel = fused && sizeof(R) == 4 && !S.scan_incoherent && !(a.flags & 8);
+    const int g_walk = persistent_grid((const void *)extend_walk_kernel<R>, T, smem);
     g_simple = persistent_grid((const void *)accumulate_kernel<R>, T, 0);
 
     if (std::is_same<Rng, RefRng>::value) {
@@ -151,7 +156,9 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     }
     cudaError_t e;
     // camera rays are generated inside the first bounce kernel when the RNG is counter-based
-    const bool fuse_primary = fused && std::is_same<Rng, PcgRng>::value;
+    // (large scenes, flag 32: the primary rays go through raygen + the persistent walk kernel as well — measured
+    // 172.4 vs 169.3 ms per step on the 1 M-triangle scene, so the fused first bounce stays the default)
+    const bool fuse_primary = fused && std::is_same<Rng, PcgRng>::value && !(walk_kernel && (a.flags & 32));
     const int g_primary = persistent_grid((const void *)shade_kernel<R, PcgRng, 4>, T, smem_bvh);
     const int g_primary_small = planar ? persistent_grid((const void *)shade_kernel<R, PcgRng, 6>, T, smem_bvh_small) : 0;
     // small scenes: primary rays use the scan/box records too unless B2RT_PATH_PRIMARY_WALK asks for the LBVH walk
@@ -181,6 +188,14 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 else shade_kernel<R, PcgRng, 4><<<g_primary, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth, PA);
                 prof_end(st);
                 launches -= 1;
+            } else if (walk_kernel) {
+                prof_begin(kExtend, st);
+                extend_walk_kernel<R><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
+                                                                (unsigned *)(fetch + b));
+                prof_end(st);
+                prof_begin(kShade, st);
+                shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);
+                prof_end(st);
             } else if (fused) {
                 prof_begin(kShade, st);
                 if (scan && planar) shade_kernel<R, Rng, 3><<<g_fuse_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth, PA);
