@@ -68,7 +68,10 @@ cudaError_t Api<R>::whitted_texture(const b2rt_scene *s, const double *cam, int 
     SceneDev S = make_scene_dev(s);
     Cam<R> c = make_cam<R>(cam);
     int n = W * H, T = 128;
-    whitted_texture_kernel<R><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, spp, max_depth, rgb, u8);
+    if (sizeof(R) == 4 && S.scan_incoherent && S.n_scan > 0 && S.surf)
+        whitted_texture_kernel<R, true><<<(n + T - 1) / T, T, smem_scan_bytes(S) + smem_surf_bytes(S), st>>>(S, c, W, H, spp, max_depth, rgb, u8);
+    else
+        whitted_texture_kernel<R, false><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, spp, max_depth, rgb, u8);
     return cudaGetLastError();
 }
 

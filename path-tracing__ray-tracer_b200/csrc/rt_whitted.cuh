@@ -148,15 +148,24 @@ whitted_cpu_kernel(SceneDev S, Cam<R> cam, int W, int H, const double *jitter, i
 }
 
 // ------------------------------------------------------------------ cuda_trace_ray (textured Whitted)
-template <typename R>
-__device__ __forceinline__ V3<R> trace_ray_texture(const SceneDev &S, const float4 *s_top, Ray<R> r, int max_depth) {
+// SMALL (float32, small scenes): closest hits and the 16 shadow rays per hit scan the box / planar records and
+// shading reads the surface records, all staged in shared memory (s_top then points at the scan records);
+// otherwise the LBVH is walked with its top levels in s_top.
+template <typename R, bool SMALL>
+__device__ __forceinline__ V3<R> trace_ray_texture(const SceneDev &S, const float4 *s_top, const float4 *s_surf, Ray<R> r,
+                                                   int max_depth) {
     V3<R> col = {R(0), R(0), R(0)}, att = {R(1), R(1), R(1)};
     const R nl = R(S.n_lights);
     for (int depth = 0; depth < max_depth; ++depth) {
         Hit<R> h;
-        if (!traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h)) break;
         Surface<R> sf;
-        make_surface<R, false>(S, r, h, sf);
+        if constexpr (SMALL && sizeof(R) == 4) {
+            if (!scan_small<false>(S, s_top, r, 0.001f, 1000000.0f, h)) break;
+            make_surface_small(s_surf, r, h, sf);
+        } else {
+            if (!traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h)) break;
+            make_surface<R, false>(S, r, h, sf);
+        }
         V3<R> mc = base_color<R, false>(S, sf);
         V3<R> local = mc * R(0.4);                                                    // :222-225
         if (S.n_lights > 0) {
@@ -169,7 +178,9 @@ __device__ __forceinline__ V3<R> trace_ray_texture(const SceneDev &S, const floa
                 l = l / ld;
                 Ray<R> sr; sr.o = sf.p + sf.n * R(0.001); sr.d = l;
                 Hit<R> sh;
-                if (traverse<R, false, true>(S, s_top, sr, R(0.001), ld - R(0.001), sh)) continue;
+                if constexpr (SMALL && sizeof(R) == 4) {
+                    if (scan_small<true>(S, s_top, sr, 0.001f, ld - 0.001f, sh)) continue;
+                } else if (traverse<R, false, true>(S, s_top, sr, R(0.001), ld - R(0.001), sh)) continue;
                 R ndl = sf.n.x * l.x + sf.n.y * l.y + sf.n.z * l.z;
                 R df = max_(R(0), ndl);
                 R atten = R(1.5) / (R(1.0) + R(0.001) * ld + R(0.0001) * ld * ld);
@@ -227,10 +238,15 @@ __device__ __forceinline__ uint8_t quant8(double c) {      // min(255, max(0, in
     return (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
 }
 
-template <typename R>
+template <typename R, bool SMALL>
 __global__ void __launch_bounds__(128)
 whitted_texture_kernel(SceneDev S, Cam<R> cam, int W, int H, int spp, int max_depth, double *rgb, uint8_t *u8) {
-    stage_top(S, smem_top);
+    const float4 *s_surf = nullptr;
+    if (SMALL) {
+        stage_scan(S, smem_top);
+        stage_surf(S, smem_top + 4 * (S.n_scan + S.n_box));
+        s_surf = smem_top + 4 * (S.n_scan + S.n_box);
+    } else stage_top(S, smem_top);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W * H) return;
     int x = i % W, y = i / W;
@@ -245,7 +261,7 @@ whitted_texture_kernel(SceneDev S, Cam<R> cam, int W, int H, int spp, int max_de
             R du = (R(a) + rnd) / R(grid_n), dv = (R(b) + rnd) / R(grid_n);
             rng = (rng * 1103515245LL + 12345LL) & 0x7fffffffLL;
             Ray<R> r = camera_ray<R>(cam, (R(x) + du) / R(W), (R(y) + dv) / R(H));
-            V3<R> s = trace_ray_texture<R>(S, smem_top, r, max_depth);
+            V3<R> s = trace_ray_texture<R, SMALL>(S, smem_top, s_surf, r, max_depth);
             c = c + s;
             rng = (rng * 1103515245LL + 12345LL) & 0x7fffffffLL;
         }

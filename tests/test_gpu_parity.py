@@ -224,6 +224,24 @@ def test_whitted_texture_vs_reference_golden(scene, cornell, golden_dir, name):
     assert np.array_equal(img, u8[::-1])
 
 
+@pytest.mark.parametrize("name", ["nb_texture_96x54_spp4_d6", "nb_texture_64x48_spp9_d16"])
+def test_whitted_texture_f32_production_close_to_reference(scene, cornell, golden_dir, name):
+    """The float32 production instantiation of the textured Whitted renderer (box / planar scan records and
+    shared-memory surface records for the Cornell box) against the reference's golden output: deterministic
+    image, so every pixel away from a silhouette agrees to a quantisation level."""
+    g = np.load(f"{golden_dir}/{name}.npz")
+    W, H, SPP, D = (int(v) for v in g["params"])
+    cam = cornell[1].create_camera(W / H)
+    r = renderer.B200TextureRaytracer(precision="f32")
+    rgb, u8 = r.render_float(scene, cam, RenderSettings(W, H, SPP, D))
+    d = np.abs(u8.astype(int) - g["u8"].astype(int)).max(axis=2)
+    assert (d <= 1).mean() > 0.985, f"{(d > 1).sum()} of {d.size} pixels differ by more than one level"
+    assert np.median(d) == 0
+    _, ref_f, _ = O.nb_whitted_texture(O.nb_pack(scene, cam), W, H, SPP, D)
+    err = np.abs(rgb - ref_f).max(axis=2)
+    assert np.quantile(err, 0.97) < 2e-3
+
+
 # ------------------------------------------------------------------------------------ path tracer (c)
 @pytest.mark.parametrize("fc", [0, 1])
 def test_path_reference_rng_f64_replays_reference(scene, cam169, golden_dir, fc):
