@@ -33,7 +33,7 @@ class SceneStruct(C.Structure):
         ("d_bvh_nodes", C.c_void_p), ("d_bvh_top", C.c_void_p),
         ("n_bvh_top", C.c_int32), ("bvh_root", C.c_int32), ("scan_incoherent", C.c_int32), ("n_scan_prims", C.c_int32), ("d_scan_prims", C.c_void_p), ("d_occluder_hint", C.c_void_p), ("ray_sort_extent", C.c_float),
         ("n_scan_loose", C.c_int32), ("n_scan_boxes", C.c_int32), ("reserved_", C.c_int32),
-        ("d_surface_records", C.c_void_p),
+        ("d_surface_records", C.c_void_p), ("bounds_lo", C.c_float * 3), ("bounds_hi", C.c_float * 3),
     ]
 
 

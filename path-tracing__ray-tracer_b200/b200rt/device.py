@@ -174,6 +174,9 @@ class DeviceScene:
         s.scan_incoherent = 1 if scan_ok else 0
         s.ray_sort_extent = float(packed.max_abs_coordinate()) if (not scan_ok and packed.n_prims >= ray_sort_min_prims) else 0.0
         s.n_scan_prims, s.d_scan_prims, s.d_occluder_hint, s.d_surface_records = 0, None, None, None
+        blo, bhi = packed.bounds()
+        for k in range(3):
+            s.bounds_lo[k], s.bounds_hi[k] = float(blo[k]), float(bhi[k])
         if self.scan_host is not None:
             self.scan_prims = d["scan"]
             s.n_scan_prims, s.d_scan_prims = self.scan_host.shape[0] // 4, self.scan_prims.data_ptr()

@@ -135,6 +135,27 @@ class PackedScene:
     def n_tex(self) -> int:
         return int(self.tex_info.shape[0])
 
+    def bounds(self, pad_rel: float = 1e-4):
+        """(lo[3], hi[3]) of all primitives, padded outward (float32).  An empty scene gives lo > hi."""
+        lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+        if self.n_rect:
+            r = self.rect.reshape(-1, 4, 4)
+            a = r[:, 0, :3]
+            u, v = r[:, 2, :3] * r[:, 0, 3:4], r[:, 3, :3] * r[:, 1, 3:4]
+            for c in (a, a + u, a + v, a + u + v):
+                lo, hi = np.minimum(lo, c.min(0)), np.maximum(hi, c.max(0))
+        if self.n_sphere:
+            sp = self.sphere.reshape(-1, 2, 4)
+            lo = np.minimum(lo, (sp[:, 0, :3] - sp[:, 0, 3:4]).min(0)); hi = np.maximum(hi, (sp[:, 0, :3] + sp[:, 0, 3:4]).max(0))
+        if self.n_tri:
+            t = self.tri.reshape(-1, 3, 4)
+            for c in (t[:, 0, :3], t[:, 0, :3] + t[:, 1, :3], t[:, 0, :3] + t[:, 2, :3]):
+                lo, hi = np.minimum(lo, c.min(0)), np.maximum(hi, c.max(0))
+        if not np.all(np.isfinite(lo)):
+            return np.ones(3, np.float32), -np.ones(3, np.float32)
+        pad = pad_rel * max(float(np.abs(lo).max()), float(np.abs(hi).max()), 1e-3)
+        return (lo - pad).astype(np.float32), (hi + pad).astype(np.float32)
+
     def max_abs_coordinate(self) -> float:
         m = 0.0
         if self.n_rect:

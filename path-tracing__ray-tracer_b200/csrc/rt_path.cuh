@@ -534,7 +534,11 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             } else if (MODE == 2) {
                 scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
             } else {
-                if constexpr (sizeof(R) == 4) scan_small<false>(S, s_scan, r, 0.001f, 1000000.0f, h);
+                if constexpr (sizeof(R) == 4) {
+                    // camera rays: one slab test of the scene bounds answers the (coherent) misses
+                    if (PRIMARY && misses_scene(S, r)) { h.t = 1000000.0f; h.prim = -1; h.a = 0.f; h.b = 0.f; }
+                    else scan_small<false>(S, s_scan, r, 0.001f, 1000000.0f, h);
+                }
             }
             shade_segment<R, Rng, PRIMARY, (WALK || MODE == 0) && !(sizeof(R) == 4 && MODE == 6), SURF>(S, Q, (PLANAR && !S.occl_hint) ? nullptr : s_scan, s_surf,
                                                                 r, h, slot, bounce, max_depth, g);

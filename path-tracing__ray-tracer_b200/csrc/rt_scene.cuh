@@ -47,6 +47,7 @@ struct SceneDev {
     const int *occl_hint;
     const float4 *surf;                // per-primitive shading records of small float32 scenes (or nullptr)
     float sort_inv;                    // 0.5 / ray_sort_extent, or 0 when ray sorting is off
+    float blo[3], bhi[3];              // padded scene bounds (blo > bhi: unknown)
 };
 
 inline SceneDev make_scene_dev(const b2rt_scene *s) {
@@ -69,6 +70,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.scan = reinterpret_cast<const float4 *>(s->d_scan_prims);
     d.occl_hint = s->precision == B2RT_PRECISION_F32 ? s->d_occluder_hint : nullptr;
     d.surf = s->precision == B2RT_PRECISION_F32 ? reinterpret_cast<const float4 *>(s->d_surface_records) : nullptr;
+    for (int k = 0; k < 3; ++k) { d.blo[k] = s->bounds_lo[k]; d.bhi[k] = s->bounds_hi[k]; }
     d.sort_inv = (s->ray_sort_extent > 0.f && !s->scan_incoherent) ? 0.5f / s->ray_sort_extent : 0.f;
     return d;
 }
@@ -450,6 +452,18 @@ __device__ __forceinline__ void scan_resolve_face(const float4 *sp, int k, float
         u = a; v = b;
     }
     best.prim = id; best.a = u; best.b = v;
+}
+
+// slab test of the whole scene (camera rays start outside it)
+__device__ __forceinline__ bool misses_scene(const SceneDev &S, const Ray<float> &r) {
+    if (S.blo[0] > S.bhi[0]) return false;
+    const float ix = rcp_approx(r.d.x), iy = rcp_approx(r.d.y), iz = rcp_approx(r.d.z);
+    const float x0 = (S.blo[0] - r.o.x) * ix, x1 = (S.bhi[0] - r.o.x) * ix;
+    const float y0 = (S.blo[1] - r.o.y) * iy, y1 = (S.bhi[1] - r.o.y) * iy;
+    const float z0 = (S.blo[2] - r.o.z) * iz, z1 = (S.bhi[2] - r.o.z) * iz;
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return tn > tf;
 }
 
 template <bool AnyHit>
