@@ -231,3 +231,75 @@ def test_cli_renders_with_the_reference_flags(tmp_path):
     out2 = tmp_path / "cli2.png"
     assert cli.main(["-r", "b200_texture_raytracer", "-w", "64", "--height", "48", "-s", "4", "-d", "4", "-o", str(out2)]) == 0
     assert Image.open(out2).size == (64, 48)
+
+
+def _sheared_open_box_scene(seed=3):
+    """A sheared parallelepiped made of triangle pairs with ONE face missing, a rotated cube made of rectangles,
+    two spheres and a few loose triangles."""
+    rng = np.random.default_rng(seed)
+    sc = Scene()
+    m = Material(Vec3(0.7, 0.6, 0.5), diffuse=0.8)
+    c = np.array([1.0, -2.0, 0.5])
+    h = [np.array([3.0, 0.4, 0.2]), np.array([0.5, 2.5, -0.3]), np.array([-0.2, 0.6, 2.0])]      # sheared half axes
+    V = lambda p: Vec3(*[float(x) for x in p])
+    for k in range(3):
+        i, j = (k + 1) % 3, (k + 2) % 3
+        for sgn in (-1, 1):
+            if k == 2 and sgn == 1:
+                continue                                     # the open face
+            p0 = c + sgn * h[k] - h[i] - h[j]
+            p1, p3 = p0 + 2 * h[i], p0 + 2 * h[j]
+            p2 = p1 + p3 - p0
+            sc.add_object(Triangle(V(p0), V(p1), V(p2), None, None, None, m))
+            sc.add_object(Triangle(V(p0), V(p2), V(p3), None, None, None, m))
+    # rotated cube of rectangles
+    a = 0.6
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    cc, s = np.array([-5.0, 1.0, -1.0]), 1.5
+    ax = [R[:, 0], R[:, 1], R[:, 2]]
+    for k in range(3):
+        i, j = (k + 1) % 3, (k + 2) % 3
+        for sgn in (-1, 1):
+            anchor = cc + sgn * s * ax[k] - s * ax[i] - s * ax[j]
+            sc.add_object(Plane(V(anchor), V(sgn * ax[k]), V(ax[i]), V(ax[j]), 2 * s, 2 * s, m))
+    sc.add_object(Sphere(Vec3(0.5, -2.0, 0.3), 0.8, m))       # inside the sheared box
+    sc.add_object(Sphere(Vec3(4.0, 4.0, 4.0), 1.1, m))
+    for _ in range(3):
+        q = rng.uniform(-6, 6, 3)
+        p = [V(q + rng.normal(scale=1.5, size=3)) for _ in range(3)]
+        sc.add_object(Triangle(p[0], p[1], p[2], None, None, None, m))
+    sc.lights = [Vec3(0.0, 8.0, 0.0)]
+    return sc
+
+
+def test_box_records_on_sheared_open_box_and_rotated_cube():
+    """group_scan_boxes on a sheared parallelepiped of triangle pairs with a missing face and a rotated cube of
+    rectangles: two box records; the box scan equals the one-by-one planar scan and the float64 generic scan for
+    rays from outside, from inside either box and through the open face."""
+    sc = _sheared_open_box_scene()
+    pk = packer.pack_scene(sc, "numba")
+    quads = []
+    rec = packer.build_scan_prims(pk, quads_out=quads)
+    rec2, n_loose, boxes = packer.group_scan_boxes(rec, quads)
+    boxes = boxes.reshape(-1, 4, 4)
+    assert boxes.shape[0] == 2
+    codes = [sorted(int(x) for x in b[3, :2].view(np.uint8)[:6]) for b in boxes]
+    assert sorted(sum(1 for x in cds if x != 255) for cds in codes) == [5, 6]
+    assert n_loose == 3                                        # the loose triangles
+    rng = np.random.default_rng(2)
+    n = 120000
+    o = rng.uniform(-9, 9, size=(n, 3))
+    o[: n // 4] = np.array([1.0, -2.0, 0.5]) + rng.uniform(-0.8, 0.8, size=(n // 4, 3))      # inside the sheared box
+    o[n // 4: n // 2] = np.array([-5.0, 1.0, -1.0]) + rng.uniform(-1.0, 1.0, size=(n // 4, 3))   # inside the cube
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    a, ra = renderer.trace_rays(sc, o, d, "numba", "f32", use_bvh=2, scan_boxes=True)
+    b, rb = renderer.trace_rays(sc, o, d, "numba", "f32", use_bvh=2, scan_boxes=False)
+    g, rg = renderer.trace_rays(sc, o, d, "numba", "f64", use_bvh=0)
+    assert (a == b).mean() > 0.9995 and (a == g).mean() > 0.999
+    both = (a == g) & (g >= 0)
+    cos = np.abs((rg[both, 4:7] * d[both]).sum(1))
+    tol = 2e-5 * np.maximum(1.0, rg[both, 0]) + 8e-6 / np.maximum(cos, 1e-6)
+    assert (np.abs(ra[both, 0] - rg[both, 0]) <= tol).all()
+    assert (g >= 0).mean() > 0.5
+    occ, _ = renderer.trace_rays(sc, o, d, "numba", "f32", use_bvh=2, any_hit=True, scan_boxes=True)
+    assert np.mean((occ >= 0) == (g >= 0)) > 0.9995
