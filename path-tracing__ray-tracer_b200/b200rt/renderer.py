@@ -36,19 +36,24 @@ def _torch_real(precision: int):
 class _TextureCache:
     """Device copies of the textures as RGBX8 (one 32-bit load per texel).
 
-    The decoded ``Texture.pixels`` (RGB8) are copied into the pinned staging buffer, shipped with one H2D
-    copy and expanded to RGBX on the device.  Keyed by the identity of the pixel arrays; ``enabled=False``
-    re-uploads on every call (what bench.py's end-to-end leg does)."""
+    Two levels.  (1) A persistent PINNED host copy of the decoded ``Texture.pixels`` (RGB8, all textures back to
+    back), rebuilt only when the pixel arrays change identity — the reference re-reads and re-flattens its textures
+    on every ``render()`` (``cuda_path_tracer.py:901-932``: 4.7 s of Python list building).  (2) The device copy:
+    one H2D copy of that pinned block plus a handful of elementwise kernels that expand RGB to RGBX.
+    ``enabled=False`` drops level 2, i.e. the textures are re-uploaded from pinned memory on every call (what
+    bench.py's end-to-end leg does)."""
 
     def __init__(self, enabled: bool = True):
         self.enabled = enabled
         self._key = None
         self._val = None
         self._host = None
+        self._pin_key = None
+        self._pinned = None
+        self._info = None
         self.uploaded_bytes = 0
 
     def get(self, scene, device):
-        from .device import Blob
         from .packer import texture_paths_sorted
         texs = {}
         for o in scene.objects:
@@ -56,28 +61,38 @@ class _TextureCache:
             if t is not None and getattr(t, "path", None):
                 texs.setdefault(t.path, t)
         paths = texture_paths_sorted(scene)
-        key = (tuple((p, id(texs[p].pixels), texs[p].pixels.shape) for p in paths), str(device))
+        pin_key = tuple((p, id(texs[p].pixels), texs[p].pixels.shape) for p in paths)
+        key = (pin_key, str(device))
         if self.enabled and key == self._key:
             self.uploaded_bytes = 0
             return self._host, self._val
-        info, off = [], 0
-        blob = Blob()
-        for i, p in enumerate(paths):
-            px = np.ascontiguousarray(texs[p].pixels, dtype=np.uint8)
-            h, w = px.shape[:2]
-            info.append((off, w, h, 0))
-            off += h * w
-            blob.add(f"t{i}", px[..., :3].reshape(-1))
-        tex_info = np.array(info, dtype=np.int32).reshape(-1, 4)
-        blob.add("info", tex_info if len(info) else np.zeros((1, 4), np.int32))
-        d = blob.upload(device)
-        texels = torch.empty(max(1, off), dtype=torch.int32, device=device)
-        for i, (o_, w, h, _) in enumerate(info):          # RGB8 -> RGBX8 on the device (plumbing, not the hot path)
-            rgb = d[f"t{i}"].view(-1, 3).to(torch.int32)
-            texels[o_:o_ + w * h] = rgb[:, 0] | (rgb[:, 1] << 8) | (rgb[:, 2] << 16) | (255 << 24)
-        host = (None, tex_info, {p: i for i, p in enumerate(paths)})
-        self._key, self._val, self._host = key, (texels, d["info"]), host
-        self.uploaded_bytes = int(blob.nbytes)
+        if pin_key != self._pin_key:                        # (1) pinned host block
+            info, off = [], 0
+            for p in paths:
+                h, w = texs[p].pixels.shape[:2]
+                info.append((off, w, h, 0))
+                off += h * w
+            self._info = np.array(info, dtype=np.int32).reshape(-1, 4) if info else np.zeros((1, 4), np.int32)
+            self._info_off = (3 * off + 255) & ~255       # the (offset, w, h) table rides behind the texels
+            pinned = torch.empty(self._info_off + self._info.nbytes, dtype=torch.uint8, pin_memory=True)
+            hv = pinned.numpy()
+            hv[self._info_off:] = self._info.reshape(-1).view(np.uint8)
+            for (o_, w, h, _), p in zip(info, paths):
+                hv[3 * o_: 3 * (o_ + w * h)] = np.ascontiguousarray(texs[p].pixels, dtype=np.uint8)[..., :3].reshape(-1)
+            self._pinned, self._pin_key = pinned, pin_key
+            self._n_texels = off
+        n = self._n_texels
+        # (2) one H2D copy + RGB8 -> RGBX8 on the device (plumbing, not the hot path)
+        rgb8 = torch.empty(self._pinned.numel(), dtype=torch.uint8, device=device)
+        rgb8.copy_(self._pinned, non_blocking=True)
+        texels = torch.empty(max(1, n), dtype=torch.int32, device=device)
+        if n:
+            rgb = rgb8[: 3 * n].view(-1, 3).to(torch.int32)
+            texels[:n] = rgb[:, 0] | (rgb[:, 1] << 8) | (rgb[:, 2] << 16) | (255 << 24)
+        info_dev = rgb8[self._info_off:].view(torch.int32)
+        host = (None, self._info, {p: i for i, p in enumerate(paths)})
+        self._key, self._val, self._host = key, (texels, info_dev), host
+        self.uploaded_bytes = int(self._pinned.numel())
         return host, self._val
 
 
@@ -122,7 +137,8 @@ class _B200Base(BaseRenderer):
             host = self._host_img = torch.empty(n, dtype=torch.uint8, pin_memory=True)
         host[:n].copy_(u8.reshape(-1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return Image.fromarray(host[:n].numpy().reshape(height, width, 3).copy(), "RGB")
+        # frombytes decodes into the image's own storage: exactly one copy out of the reused pinned buffer
+        return Image.frombytes("RGB", (width, height), memoryview(host[:n].numpy()))
 
 
 # ------------------------------------------------------------------------------------------ path tracer
