@@ -314,3 +314,43 @@ def test_box_grouping_leaves_unrelated_quads_alone():
     rec0 = packer.build_scan_prims(pk, quads_out=quads)
     rec, n_loose, boxes = packer.group_scan_boxes(rec0, quads)
     assert n_loose == 2 and boxes.shape[0] == 0 and np.array_equal(rec, rec0)
+
+
+def test_surface_records_and_bounds(cornell):
+    """packer.build_surface_records: one 5-float4 record per primitive restating what cuda_scene_hit returns beside t
+    (normal / sphere centre, material, affine uv map); PackedScene.bounds contains every primitive."""
+    from b200rt import packer
+    pk = packer.pack_scene(cornell[0], "numba")
+    rec = packer.build_surface_records(pk).reshape(-1, 5, 4)
+    assert rec.shape[0] == pk.n_prims == 34
+    R, S, SH = pk.rect.reshape(-1, 4, 4), pk.sphere.reshape(-1, 2, 4), pk.shade.reshape(-1, 3, 4)
+    M = pk.mat.reshape(-1, 2, 4)
+    flags = rec[:, 4, 3].view(np.int32)
+    tex = rec[:, 3, 3].view(np.int32)
+    for k in range(pk.n_prims):
+        m = pk.prim_mat[k]
+        assert np.array_equal(rec[k, 1], M[m, 0].astype(np.float32)) and np.array_equal(rec[k, 2], M[m, 1].astype(np.float32))
+        assert tex[k] == pk.mat_tex[m]
+    for i in range(pk.n_rect):                       # u = a / u_len, v = b / v_len, never flipped
+        assert np.array_equal(rec[i, 0, :3], R[i, 1, :3].astype(np.float32)) and rec[i, 0, 3] == 0 and flags[i] == 0
+        a, b = 0.3 * R[i, 0, 3], 0.8 * R[i, 1, 3]
+        u = rec[i, 3, 0] + a * rec[i, 3, 1] + b * rec[i, 3, 2]
+        v = rec[i, 4, 0] + a * rec[i, 4, 1] + b * rec[i, 4, 2]
+        assert abs(u - 0.3) < 1e-6 and abs(v - 0.8) < 1e-6
+    for i in range(pk.n_sphere):                     # centre + 1/r: n = (p - c) / r
+        k = pk.n_rect + i
+        assert np.array_equal(rec[k, 0, :3], S[i, 0, :3].astype(np.float32)) and abs(rec[k, 0, 3] * S[i, 0, 3] - 1) < 1e-6
+    base = pk.n_rect + pk.n_sphere
+    for i in range(pk.n_tri):                        # w uv0 + a uv1 + b uv2 (cuda_path_tracer.py:722-724), flipped to face the ray
+        k = base + i
+        assert flags[k] == 1
+        uv0, uv1, uv2 = SH[k, 1, 0:2], SH[k, 1, 2:4], SH[k, 2, 0:2]
+        a, b = 0.25, 0.6
+        want = (1 - a - b) * uv0 + a * uv1 + b * uv2
+        got = np.array([rec[k, 3, 0] + a * rec[k, 3, 1] + b * rec[k, 3, 2], rec[k, 4, 0] + a * rec[k, 4, 1] + b * rec[k, 4, 2]])
+        assert np.abs(got - want).max() < 1e-6
+    lo, hi = pk.bounds()
+    assert (lo < -15).all() and (lo > -15.1).all() and (hi[:2] > 15).all() and (hi < 15.1).all()
+    from b200rt.scene_api import Scene
+    elo, ehi = packer.pack_scene(Scene(), "numba").bounds()
+    assert (elo > ehi).all()                         # empty scene: "unknown"
