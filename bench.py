@@ -40,8 +40,8 @@ FLOPS_PER_RAY = 1070.0          # reference-algorithm intersection cost per ray 
 QUEUE_RECORD_BYTES = 48.0       # one ray-queue or shadow-queue record (3 float4 streams)
 STEP_BYTES_PER_PATH = 550.0     # whole-wavefront queue traffic per path
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused bounce kernel, averaged over the 8 bounce launches of one
-# 32-spp wave at 1080p (ncu --set full, profiles/r1d_ncu_full_one_wave_32spp.csv: 13.09 GB per wave)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 13.090496e9 / 8
+# 32-spp wave at 1080p (ncu --set full, profiles/r1e_ncu_full_one_wave_32spp.csv: 13.08 GB per wave)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 13.075816e9 / 8
 
 
 def build_scene():
