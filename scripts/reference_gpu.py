@@ -42,4 +42,25 @@ try:
         img.save(os.path.join(ROOT, "gpurun_out", "b200rt_same_scene.png")) if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
 except Exception as e:
     out["b200rt_error"] = f"{type(e).__name__}: {e}"[:400]
+# ---- the reference's default renderer (cuda_texture_raytracer) at its golden setting: 2000x1500, 25 spp, depth 16
+try:
+    if scene is not None:
+        import numpy as np
+        import renderers.cuda_texture_renderer  # noqa: F401
+        W2, H2, S2, D2 = 2000, 1500, 25, 16
+        cam2 = b.create_camera(W2 / H2)
+        tref = RendererFactory.create("cuda_texture_raytracer")
+        t0 = time.perf_counter(); tref.render(scene, cam2, RenderSettings(W2, H2, 1, D2)); jit = time.perf_counter() - t0
+        t0 = time.perf_counter(); img_ref = tref.render(scene, cam2, RenderSettings(W2, H2, S2, D2)); t_ref = time.perf_counter() - t0
+        res = {"reference_render_s": t_ref, "reference_first_call_incl_jit_s": jit}
+        for prec in ("f64", "f32"):
+            tours = RendererFactory.create("b200_texture_raytracer", precision=prec)
+            tours.render(scene, cam2, RenderSettings(W2, H2, S2, D2))
+            t0 = time.perf_counter(); img = tours.render(scene, cam2, RenderSettings(W2, H2, S2, D2)); dt = time.perf_counter() - t0
+            d = np.abs(np.asarray(img).astype(int) - np.asarray(img_ref).astype(int)).max(axis=2)
+            res[prec] = {"render_s": dt, "pixels_differing": int((d > 0).sum()), "pixels_differing_by_more_than_1": int((d > 1).sum()),
+                         "of": int(d.size)}
+        out["texture_raytracer_2000x1500_25spp_d16"] = res
+except Exception as e:
+    out["texture_error"] = f"{type(e).__name__}: {e}"[:400]
 print(json.dumps(out))
