@@ -174,6 +174,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         Q.perm = nullptr;
         PrimaryArgs<R> PA;
         PA.cam = c; PA.W = W; PA.H = H; PA.spp_wave = k; PA.first_sample = a.sample_offset + done; PA.seed = a.seed;
+        PA.by_npix = FastDiv::make((unsigned)npix); PA.by_w = FastDiv::make((unsigned)W);
         if ((e = cudaMemsetAsync(counts, 0, counts_bytes, st))) return e;
         if (!fuse_primary) {
             prof_begin(kRaygen, st);

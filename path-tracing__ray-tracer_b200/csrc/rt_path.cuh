@@ -463,9 +463,31 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
 #ifndef B2RT_OPT_SURF
 #define B2RT_OPT_SURF 1
 #endif
+// Exact unsigned division by a launch-invariant divisor: one multiply-high + shift (the generic 32-bit division of
+// i / npix, pix / W costs ~20 instructions each, ~50 of the ~600 a camera-ray warp issues).  Round-up method of
+// Granlund & Montgomery / libdivide "branchfree": q = (t + ((n - t) >> 1)) >> (sh - 1) with t = mulhi(n, m).
+struct FastDiv {
+    unsigned d, m, sh;
+    static FastDiv make(unsigned d) {
+        FastDiv f; f.d = d; f.m = 0; f.sh = 0;
+        if (d <= 1) return f;
+        unsigned sh = 0;
+        while ((1ull << sh) < d) ++sh;
+        f.sh = sh;
+        f.m = (unsigned)(((1ull << 32) * ((1ull << sh) - d)) / d + 1);
+        return f;
+    }
+    __device__ __forceinline__ unsigned div(unsigned n) const {
+        if (d <= 1) return n;
+        const unsigned t = __umulhi(n, m);
+        return (t + ((n - t) >> 1)) >> (sh - 1);
+    }
+};
+
 template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fused into the first bounce
     Cam<R> cam;
     int W, H, spp_wave;
+    FastDiv by_npix, by_w;
     long long first_sample;
     unsigned long long seed;
 };
@@ -509,8 +531,8 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         if (valid) {
             Ray<R> r;
             if (PRIMARY) {                       // cuda_path_trace_kernel's sample set-up (:35-41)
-                const int npix = P.W * P.H, pix = i % npix, s = i / npix;
-                const int x = pix % P.W, y = pix / P.W;
+                const int npix = P.W * P.H, s = (int)P.by_npix.div((unsigned)i), pix = i - s * npix;
+                const int y = (int)P.by_w.div((unsigned)pix), x = pix - y * P.W;
                 uint64_t state = PcgRng::seed((uint32_t)pix, (uint64_t)(P.first_sample + s), P.seed);
                 R rnd = PcgRng::template random<R>(state);
                 state = PcgRng::advance(state);
