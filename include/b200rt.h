@@ -117,7 +117,7 @@ typedef struct b2rt_scene {
      * With n_scan_boxes == 0 set n_scan_loose = n_scan_prims. */
     int32_t n_scan_loose;
     int32_t n_scan_boxes;
-    int32_t reserved_;
+    int32_t bvh_rects_outside;   /* 1: the hierarchy was built with B2RT_LBVH_RECTS_OUTSIDE */
     /* Optional (small float32 scenes; NULL otherwise): float4[5*n_prims] per-primitive shading records, staged in
      * shared memory by the bounce kernels (packer.build_surface_records) — one branch-free, one-hop record instead
      * of the per-type branches and the prim -> material -> texture chain of dependent loads:
@@ -148,7 +148,11 @@ int b2rt_lbvh_temp_bytes(int32_t n_prims, size_t *h_bytes);
 int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri,
                     const void *d_rect_f32, const void *d_sphere_f32, const void *d_tri_f32,
                     float box_pad, void *d_nodes_out, void *d_top_out, int32_t top_capacity,
-                    int32_t *h_meta_out, void *d_temp, size_t temp_bytes, void *stream);
+                    int32_t *h_meta_out, void *d_temp, size_t temp_bytes, void *stream, int32_t flags);
+/* flags for b2rt_lbvh_build */
+#define B2RT_LBVH_RECTS_OUTSIDE 1 /* the rectangles get no place in the hierarchy (set b2rt_scene.bvh_rects_outside too: every
+                                     walk then tests them directly first).  For a few room-sized rectangles around a fine
+                                     mesh: inside the tree they widen every ancestor box of their leaves. */
 
 /* ---- closest hit (replaces cuda_scene_hit, cuda_path_tracer.py:496-730, and Scene.hit, core/scene.py:45) */
 /* One primary ray per pixel at sub-pixel offset (du, dv): u = (x+du)/W, v = (y+dv)/H

@@ -32,7 +32,7 @@ class SceneStruct(C.Structure):
         ("d_texels", C.c_void_p), ("d_tex_info", C.c_void_p), ("d_lights", C.c_void_p),
         ("d_bvh_nodes", C.c_void_p), ("d_bvh_top", C.c_void_p),
         ("n_bvh_top", C.c_int32), ("bvh_root", C.c_int32), ("scan_incoherent", C.c_int32), ("n_scan_prims", C.c_int32), ("d_scan_prims", C.c_void_p), ("d_occluder_hint", C.c_void_p), ("ray_sort_extent", C.c_float),
-        ("n_scan_loose", C.c_int32), ("n_scan_boxes", C.c_int32), ("reserved_", C.c_int32),
+        ("n_scan_loose", C.c_int32), ("n_scan_boxes", C.c_int32), ("bvh_rects_outside", C.c_int32),
         ("d_surface_records", C.c_void_p), ("bounds_lo", C.c_float * 3), ("bounds_hi", C.c_float * 3),
     ]
 
@@ -61,7 +61,7 @@ def load():
     SP = C.POINTER(SceneStruct)
     lib.b2rt_device_info.argtypes = [C.c_int, C.POINTER(i64)]
     lib.b2rt_lbvh_temp_bytes.argtypes = [i32, C.POINTER(sz)]
-    lib.b2rt_lbvh_build.argtypes = [i32, i32, i32, vp, vp, vp, C.c_float, vp, vp, i32, C.POINTER(i32), vp, sz, vp]
+    lib.b2rt_lbvh_build.argtypes = [i32, i32, i32, vp, vp, vp, C.c_float, vp, vp, i32, C.POINTER(i32), vp, sz, vp, i32]
     lib.b2rt_primary_hits.argtypes = [SP, C.POINTER(dbl), i32, i32, dbl, dbl, dbl, dbl, i32, vp, vp, vp]
     lib.b2rt_trace_rays.argtypes = [SP, i32, vp, vp, dbl, dbl, i32, i32, vp, vp, vp]
     lib.b2rt_render_whitted_cpu.argtypes = [SP, C.POINTER(dbl), i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(dbl), vp, vp]

@@ -98,7 +98,7 @@ class DeviceScene:
     def __init__(self, packed: PackedScene, precision: int = _lib.P_F32, device=None,
                  top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
                  scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True, ray_sort_min_prims: int = 4096,
-                 scan_boxes: bool = True, surface_records: bool = True):
+                 scan_boxes: bool = True, surface_records: bool = True, rects_outside: bool = True):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.packed = packed
@@ -156,11 +156,14 @@ class DeviceScene:
             # pad covers float32 rounding of slab distances for rays that start up to ray_origin_extent away
             pad = 1e-5 * max(packed.max_abs_coordinate(), ray_origin_extent, 1e-3)
             self.box_pad = float(pad)
+            # a few (room-sized) rectangles around a large mesh stay outside the hierarchy and are tested directly
+            self.rects_outside = bool(rects_outside and not scan_ok and 0 < packed.n_rect <= 16 and n >= 4096)
             _lib.check(self.lib.b2rt_lbvh_build(packed.n_rect, packed.n_sphere, packed.n_tri,
                                                 g_rect.data_ptr(), g_sphere.data_ptr(), g_tri.data_ptr(),
                                                 C.c_float(pad), self.nodes.data_ptr(), self.top.data_ptr(),
                                                 top_nodes, meta, temp.data_ptr(), temp.numel(),
-                                                current_stream_ptr(dev)), "b2rt_lbvh_build")
+                                                current_stream_ptr(dev), 1 if self.rects_outside else 0),
+                       "b2rt_lbvh_build")
             self.n_top, self.root, self.n_internal = int(meta[0]), int(meta[1]), int(meta[2])
         s = _lib.SceneStruct()
         s.precision, s.semantics = precision, packed.semantics
@@ -172,6 +175,7 @@ class DeviceScene:
         s.d_bvh_nodes, s.d_bvh_top = self.nodes.data_ptr(), self.top.data_ptr()
         s.n_bvh_top, s.bvh_root = self.n_top, self.root
         s.scan_incoherent = 1 if scan_ok else 0
+        s.bvh_rects_outside = 1 if self.rects_outside else 0
         s.ray_sort_extent = float(packed.max_abs_coordinate()) if (not scan_ok and packed.n_prims >= ray_sort_min_prims) else 0.0
         s.n_scan_prims, s.d_scan_prims, s.d_occluder_hint, s.d_surface_records = 0, None, None, None
         blo, bhi = packed.bounds()

@@ -91,13 +91,13 @@ int b2rt_lbvh_temp_bytes(int32_t n_prims, size_t *h_bytes) {
 
 int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri, const void *d_rect, const void *d_sphere,
                     const void *d_tri, float box_pad, void *d_nodes_out, void *d_top_out, int32_t top_capacity,
-                    int32_t *h_meta_out, void *d_temp, size_t temp_bytes, void *stream) {
+                    int32_t *h_meta_out, void *d_temp, size_t temp_bytes, void *stream, int32_t flags) {
     if (top_capacity > b2rt::kTopMax) top_capacity = b2rt::kTopMax;
     if (top_capacity < 0) top_capacity = 0;
     int meta[3];
     cudaError_t e = b2rt::lbvh_build(n_rect, n_sphere, n_tri, (const float4 *)d_rect, (const float4 *)d_sphere,
                                      (const float4 *)d_tri, box_pad, (float4 *)d_nodes_out, (float4 *)d_top_out,
-                                     top_capacity, meta, d_temp, temp_bytes, S(stream));
+                                     top_capacity, meta, d_temp, temp_bytes, S(stream), flags);
     if (e) return fail("b2rt_lbvh_build", e);
     h_meta_out[0] = meta[0]; h_meta_out[1] = meta[1]; h_meta_out[2] = meta[2];
     return 0;

@@ -69,10 +69,15 @@ __device__ Box prim_box(int i, int n_rect, int n_sphere, const float4 *rect, con
 
 __global__ void bounds_kernel(int n, int n_rect, int n_sphere, const float4 *rect, const float4 *sphere,
                               const float4 *tri, float pad, float4 *box_lo, float4 *box_hi, int *scene_bounds,
-                              double *moments) {
+                              double *moments, int n_outside) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float c[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};   // centroid bounds
-    if (i < n) {
+    const bool outside = i < n_outside;                      // kept out of the hierarchy (see lbvh_build)
+    if (outside) {
+        // a far-away point box no ray reaches; its 31-bit key sorts it behind every real primitive, so the root
+        // separates the "outside" leaves from the real tree and no real node's box is widened by them
+        box_lo[i] = box_hi[i] = make_float4(3.0e37f, 3.0e37f, 3.0e37f, 0.f);
+    } else if (i < n) {
         Box b = prim_box(i, n_rect, n_sphere, rect, sphere, tri, pad);
         box_lo[i] = make_float4(b.lo.x, b.lo.y, b.lo.z, 0.f);
         box_hi[i] = make_float4(b.hi.x, b.hi.y, b.hi.z, 0.f);
@@ -92,7 +97,7 @@ __global__ void bounds_kernel(int n, int n_rect, int n_sphere, const float4 *rec
     }
     // first and second moments of the centroids: the Morton bit allocation follows their spread per axis
     for (int k = 0; k < 6; ++k) {
-        float v = i < n ? (k < 3 ? c[k] : c[k - 3] * c[k - 3]) : 0.f;
+        float v = (i < n && !outside) ? (k < 3 ? c[k] : c[k - 3] * c[k - 3]) : 0.f;
         float r = BR(tmp).Sum(v);
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(moments + k, (double)r);
@@ -136,9 +141,10 @@ __device__ __forceinline__ uint32_t expand10(uint32_t v) {
 }
 
 __global__ void morton_kernel(int n, const float4 *box_lo, const float4 *box_hi, const int *scene_bounds,
-                              uint32_t *keys, int *vals, const double *moments, int bx, int by, int bz) {
+                              uint32_t *keys, int *vals, const double *moments, int bx, int by, int bz, int n_outside) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (i < n_outside) { keys[i] = 0x7fffffffu; vals[i] = i; return; }
     float lo[3], ext[3];
     for (int k = 0; k < 3; ++k) {
         lo[k] = ordered_to_float(scene_bounds[k]);
@@ -150,7 +156,7 @@ __global__ void morton_kernel(int n, const float4 *box_lo, const float4 *box_hi,
     float cz = (0.5f * (a.z + b.z) - lo[2]) / ext[2];
     if (bx <= 0) {                                           // automatic allocation from the centroid spread
         int bits[3];
-        morton_bits(n, moments, bits);
+        morton_bits(n - n_outside, moments, bits);
         bx = bits[0]; by = bits[1]; bz = bits[2];
     }
     if (bx == 10 && by == 10 && bz == 10) {
@@ -325,7 +331,7 @@ TempLayout layout(int n) {
     L.moments = take(64);
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const int *)nullptr, (int *)nullptr, n, 0, 30);
+                                    (const int *)nullptr, (int *)nullptr, n, 0, 31);
     L.cub_bytes = cub_bytes;
     L.cub = take(cub_bytes);
     L.total = off;
@@ -338,8 +344,11 @@ size_t lbvh_temp_bytes(int n_prims) { return layout(n_prims > 0 ? n_prims : 1).t
 
 cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, const float4 *sphere, const float4 *tri,
                        float pad, float4 *nodes, float4 *top, int top_capacity, int *h_meta, void *temp,
-                       size_t temp_bytes, cudaStream_t stream) {
+                       size_t temp_bytes, cudaStream_t stream, int build_flags) {
     int n = n_rect + n_sphere + n_tri;
+    // build_flags bit 0: the rectangles stay OUTSIDE the hierarchy (the caller tests them directly before every walk).
+    // A few room-sized rectangles inside a fine mesh would otherwise widen every ancestor box of their leaves.
+    const int n_outside = ((build_flags & 1) && n_rect < n - 1) ? n_rect : 0;
     h_meta[0] = 0; h_meta[1] = -1; h_meta[2] = 0;
     if (n <= 0) { h_meta[1] = 0; return cudaSuccess; }
     if (n == 1) { h_meta[1] = ~0; return cudaSuccess; }        // a single leaf: root = ~prim 0
@@ -367,15 +376,15 @@ cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, 
     if ((e = cudaMemsetAsync(top_id, 0xff, 4 * (size_t)(n - 1), stream))) return e;
     if ((e = cudaMemsetAsync(meta, 0, 32, stream))) return e;
     if ((e = cudaMemsetAsync(moments, 0, 64, stream))) return e;
-    bounds_kernel<<<G, T, 0, stream>>>(n, n_rect, n_sphere, rect, sphere, tri, pad, box_lo, box_hi, bounds, moments);
+    bounds_kernel<<<G, T, 0, stream>>>(n, n_rect, n_sphere, rect, sphere, tri, pad, box_lo, box_hi, bounds, moments, n_outside);
     int mb[3] = {0, 0, 0};                                   // 0: automatic (morton_bits)
     if (const char *ev = getenv("B2RT_MORTON_BITS")) {       // measurement hook: "10,10,10" forces an allocation
         if (sscanf(ev, "%d,%d,%d", &mb[0], &mb[1], &mb[2]) != 3 || mb[0] + mb[1] + mb[2] > 30 || mb[0] < 0 || mb[1] < 0 || mb[2] < 0)
             mb[0] = mb[1] = mb[2] = 0;
     }
-    morton_kernel<<<G, T, 0, stream>>>(n, box_lo, box_hi, bounds, keys_a, vals_a, moments, mb[0], mb[1], mb[2]);
+    morton_kernel<<<G, T, 0, stream>>>(n, box_lo, box_hi, bounds, keys_a, vals_a, moments, mb[0], mb[1], mb[2], n_outside);
     size_t cub_bytes = L.cub_bytes;
-    if ((e = cub::DeviceRadixSort::SortPairs(base + L.cub, cub_bytes, keys_a, keys_b, vals_a, vals_b, n, 0, 30, stream)))
+    if ((e = cub::DeviceRadixSort::SortPairs(base + L.cub, cub_bytes, keys_a, keys_b, vals_a, vals_b, n, 0, 31, stream)))
         return e;
     hierarchy_kernel<<<G, T, 0, stream>>>(n, keys_b, vals_b, children, parent_node, parent_leaf);
     refit_kernel<<<G, T, 0, stream>>>(n, children, parent_node, parent_leaf, box_lo, box_hi, flags, node_lo, node_hi, nodes);

@@ -8,5 +8,5 @@ size_t lbvh_temp_bytes(int n_prims);
 // h_meta: [0] n_top, [1] root reference, [2] internal node count.  Synchronises `stream`.
 cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, const float4 *sphere, const float4 *tri,
                        float pad, float4 *nodes, float4 *top, int top_capacity, int *h_meta, void *temp,
-                       size_t temp_bytes, cudaStream_t stream);
+                       size_t temp_bytes, cudaStream_t stream, int build_flags = 0);
 }  // namespace b2rt

@@ -231,6 +231,11 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                     best.t = R(1000000.0); best.prim = -1; best.a = R(0); best.b = R(0);
                     stack[0] = kDone; sp = 1;
                     ref = S.n_prims > 0 ? S.root : kDone;
+                    if (S.n_outside > 0) {                       // rectangles outside the hierarchy: leaves visited first
+                        stack[sp++] = ref;
+                        for (int p = S.n_outside - 1; p >= 1; --p) stack[sp++] = ~p;
+                        ref = ~0;
+                    }
                 }
             }
             exhausted = base + (unsigned)__popc(idle) >= (unsigned)n;

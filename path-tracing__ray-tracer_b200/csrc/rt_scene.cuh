@@ -42,6 +42,7 @@ struct SceneDev {
     const float4 *nodes, *top;
     int n_top, root;
     int scan_incoherent;
+    int n_outside;                     // rectangles [0, n_outside) are not in the hierarchy: tested before every walk
     int n_scan, n_loose, n_box;        // planar scan records (loose ones first), box records behind them
     const float4 *scan;
     const int *occl_hint;
@@ -64,6 +65,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.top = reinterpret_cast<const float4 *>(s->d_bvh_top);
     d.n_top = s->n_bvh_top; d.root = s->bvh_root;
     d.scan_incoherent = s->scan_incoherent;
+    d.n_outside = s->bvh_rects_outside ? s->n_rect : 0;
     d.n_scan = s->precision == B2RT_PRECISION_F32 ? s->n_scan_prims : 0;
     d.n_box = d.n_scan > 0 ? s->n_scan_boxes : 0;
     d.n_loose = d.n_box > 0 ? s->n_scan_loose : d.n_scan;
@@ -250,6 +252,11 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
     stack[0] = kDone;
     int sp = 1;
     int ref = S.root;
+    if (S.n_outside > 0) {                                       // see the if-if variant below
+        stack[sp++] = S.root;
+        for (int p = S.n_outside - 1; p >= 1; --p) stack[sp++] = ~p;
+        ref = ~0;
+    }
     while (ref != kDone) {
         while (ref >= 0) {
             float4 n0, n1, n2, n3;
@@ -289,6 +296,13 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
     int stack[kStackDepth];
     int sp = 0;
     int ref = S.root;
+    // rectangles kept outside the hierarchy (B2RT_LBVH_RECTS_OUTSIDE) are visited FIRST, as leaves stacked above the
+    // root, so a wall hit already bounds the walk (no second inlined copy of the primitive tests: that cost 10 %)
+    if (S.n_outside > 0) {
+        stack[sp++] = S.root;
+        for (int p = S.n_outside - 1; p >= 1; --p) stack[sp++] = ~p;
+        ref = ~0;
+    }
     while (true) {
         if (ref >= 0) {
             float4 n0, n1, n2, n3;

@@ -303,3 +303,28 @@ def test_box_records_on_sheared_open_box_and_rotated_cube():
     assert (g >= 0).mean() > 0.5
     occ, _ = renderer.trace_rays(sc, o, d, "numba", "f32", use_bvh=2, any_hit=True, scan_boxes=True)
     assert np.mean((occ >= 0) == (g >= 0)) > 0.9995
+
+
+def test_rectangles_outside_the_hierarchy_give_identical_hits():
+    """Large mesh + a few room-sized rectangles: the walls stay outside the LBVH (tested directly before every walk).
+    Closest and any-hit results equal the all-in-one hierarchy and the brute-force scan."""
+    from b200rt import scenes
+    scene, b = scenes.heightfield_scene(nx=121, nz=81)             # 19 200 triangles + 5 walls
+    pk = packer.pack_scene(scene, "numba")
+    rng = np.random.default_rng(8)
+    n = 60000
+    o = rng.uniform(-14, 14, (n, 3)); o[:, 1] = rng.uniform(-14.5, 14, n)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    a, ra = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=True, packed=pk, rects_outside=True)
+    c, rc = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=True, packed=pk, rects_outside=False)
+    g, rg = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=False, packed=pk)
+    assert np.array_equal(a, g) and np.array_equal(c, g)
+    assert np.array_equal(ra[:, 0], rg[:, 0]) and np.array_equal(rc[:, 0], rg[:, 0])
+    assert (g >= 0).mean() > 0.8 and ((g >= 0) & (g < 5)).mean() > 0.2    # walls (ids 0..4) are hit too
+    occ, _ = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=True, any_hit=True, packed=pk, rects_outside=True)
+    assert np.array_equal(occ >= 0, g >= 0)
+    st = RenderSettings(160, 90, 4, 4)
+    cam = b.create_camera(16 / 9)
+    x, cx = renderer.B200PathTracer(precision="f32", seed=2, rects_outside=True).render_accum(scene, cam, st)
+    y, cy = renderer.B200PathTracer(precision="f32", seed=2, rects_outside=False).render_accum(scene, cam, st)
+    assert np.array_equal(x, y) and np.array_equal(cx[:4], cy[:4])
