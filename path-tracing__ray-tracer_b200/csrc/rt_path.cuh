@@ -173,8 +173,10 @@ extend_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__res
 //     take the next rays of the (sorted) queue through one atomic per warp;
 //   * MAJORITY SCHEDULING: per iteration the warp runs either the box step or the leaf step, whichever more lanes
 //     are waiting for, so every executed instruction has at least half of the busy lanes on it.
-// Results are identical to traverse(): closest t, ties to the lowest packed id.  Hit record i belongs to queue
-// position i of the order the rays are read in (perm), which is how shade_kernel<.., 0> reads them back.
+// Results are identical to traverse(): closest t, ties to the lowest packed id.  Rays are FETCHED in sorted order
+// (perm) but hit record j is stored at the ray's own queue slot j, so the wavefront shade stage that follows reads
+// rays and hits in plain queue order with coalesced loads (gathering 64 B per ray through perm a second time made
+// that stage latency-bound: 13.5 % issue-active, ncu profiles/r1f_c4_*).
 #ifndef B2RT_WALK_REFILL
 #define B2RT_WALK_REFILL 8
 #endif
@@ -215,7 +217,7 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
         const unsigned idle = ~(mn | ml);
         if (!exhausted && (__popc(idle) >= B2RT_WALK_REFILL)) {
             if (ref == kDone && pos >= 0)
-                st_stream(hit + pos, Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b));
+                hit[pos] = Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b);
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(next, (unsigned)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -223,8 +225,8 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                 const unsigned i = base + (unsigned)__popc(idle & lt);
                 pos = -1;
                 if (i < (unsigned)n) {
-                    pos = (int)i;
                     const int j = perm ? __ldg(perm + i) : (int)i;
+                    pos = j;                                     // the hit record goes to the ray's own queue slot
                     const real4<R> a = ld_stream(ro + j), b = ld_stream(rd + j);
                     r.o = xyz<R>(a); r.d = xyz<R>(b);
                     id = {rcp_(r.d.x), rcp_(r.d.y), rcp_(r.d.z)};
@@ -283,7 +285,7 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
             ref = stack[--sp];
         }
     }
-    if (pos >= 0) st_stream(hit + pos, Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b));
+    if (pos >= 0) hit[pos] = Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b);
 }
 
 // cuda_sample_hemisphere_cosine (:139-180)
@@ -542,7 +544,8 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                 r = camera_ray<R>(P.cam, (R(x) + rnd) / R(P.W), (R(y) + rnd) / R(P.H));
                 slot = i; g.rng = state; g.thr = {R(1), R(1), R(1)};
             } else {
-                const int j = Q.perm ? __ldg(Q.perm + i) : i;          // sorted order (LBVH scenes) or queue order
+                // fused walk modes read through the sort permutation; the wavefront stage (MODE 0) reads queue order
+                const int j = (MODE != 0 && Q.perm) ? __ldg(Q.perm + i) : i;
                 real4<R> a = ld_stream(ro + j), b = ld_stream(rd + j), c = ld_stream(th + j);
                 r.o = xyz<R>(a); r.d = xyz<R>(b);
                 slot = (int)unpack_u<R>(a.w);
