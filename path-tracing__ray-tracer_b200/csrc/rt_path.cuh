@@ -1,12 +1,18 @@
 // rt_path.cuh — the wavefront path tracer (replaces cuda_path_trace_kernel + cuda_trace_path,
 // renderers/cuda_path_tracer.py:17-471).
 //
-// One WAVE = spp_per_wave samples of every pixel.  Path state lives in compacted HBM queues of real4
-// record streams; each bounce is three persistent grid-stride kernels:
-//     extend  : ray queue  -> closest hit (LBVH walk, top levels in shared memory)   -> hit stream
-//     shade   : ray+hit    -> texture, NEE shadow ray, Russian roulette, BSDF sample  -> next ray queue
-//                             (warp-ballot / prefix-popcount compaction, one atomic per warp per queue)
-//     shadow  : shadow queue -> occlusion query -> per-path radiance
+// One WAVE = spp_per_wave samples of every pixel.  Path state lives in compacted HBM queues of real4 record
+// streams; all kernels are persistent grid-stride launches.  Per bounce:
+//     shade_kernel<MODE>   closest hit + shading FUSED (camera-ray generation too at bounce 0): texture, NEE shadow-ray
+//                          emission, Russian roulette, BSDF sample -> next ray queue + shadow queue
+//                          (warp-ballot / prefix-popcount compaction, one packed 64-bit atomic per warp)
+//                          small float32 scenes: scan of box + planar records, surface records, all in shared memory
+//                          large scenes, bounce 0: LBVH walk with the top levels in shared memory
+//     extend_walk_kernel + shade_kernel<0>   large scenes, bounce >= 1: persistent walk (dynamic ray fetch, majority
+//                          scheduling) -> hit stream -> wavefront shade stage
+//     shadow_kernel        shadow queue -> occlusion query -> per-path radiance
+// and once per wave accumulate_kernel (per-pixel sums).  extend_kernel + shade_kernel<0> is the textbook unfused
+// form, kept as the measured baseline (B2RT_PATH_UNFUSED).
 // Queue record streams (16 B * 3 per path for float):
 //     ro = (origin.xyz, slot)   rd = (direction.xyz, rng state)   th = (throughput.rgb, depth)
 // Shadow records: so = (origin.xyz, slot)  sd = (direction.xyz, -)  sc = (throughput*contribution.rgb, -)
@@ -178,7 +184,7 @@ extend_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__res
 // rays and hits in plain queue order with coalesced loads (gathering 64 B per ray through perm a second time made
 // that stage latency-bound: 13.5 % issue-active, ncu profiles/r1f_c4_*).
 #ifndef B2RT_WALK_REFILL
-#define B2RT_WALK_REFILL 8
+#define B2RT_WALK_REFILL 8         // idle lanes that trigger a refill (measured 4 / 8 / 16: within 3 %)
 #endif
 #ifndef B2RT_WALK_PREFETCH
 #define B2RT_WALK_PREFETCH 0      // measured: prefetching the far child (L2) costs 10 % (126 vs 115 ms): the walk is request-bound
@@ -192,7 +198,7 @@ __device__ __forceinline__ void prefetch_tri(const SceneDev &S, int prim) {
 #define B2RT_WALK_NODE_STEPS 1     // box steps per vote (measured on 1 M triangles: 1: 115.1, 2: 117.3, 3: 122.4 ms)
 #endif
 #ifndef B2RT_WALK_MIN_BLOCKS
-#define B2RT_WALK_MIN_BLOCKS 4
+#define B2RT_WALK_MIN_BLOCKS 4     // resident CTAs/SM (47 registers; 5 measured equal)
 #endif
 template <typename R>
 __global__ void __launch_bounds__(256, sizeof(R) == 4 ? B2RT_WALK_MIN_BLOCKS : 1)
@@ -296,7 +302,7 @@ __device__ __forceinline__ V3<R> cos_hemisphere(V3<R> n, uint64_t &rng) {
     R ct = sqrt_(r1), st = sqrt_(R(1) - r1);
     R sp, cp;
 #ifndef B2RT_OPT_ONB
-#define B2RT_OPT_ONB 1
+#define B2RT_OPT_ONB 1             // 0: reference-order tangent frame + sincospif (measurement switch)
 #endif
     if constexpr (sizeof(R) == 4 && B2RT_OPT_ONB) {
         // float32 production: MUFU sin/cos on phi - pi in [-pi, pi) (abs error 2^-21; the azimuth only has to be
@@ -466,7 +472,7 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
 }
 
 #ifndef B2RT_OPT_SURF
-#define B2RT_OPT_SURF 1
+#define B2RT_OPT_SURF 1            // 0: generic make_surface in the small-scene kernels (measured 23.8 vs 22.3 ms)
 #endif
 // Exact unsigned division by a launch-invariant divisor: one multiply-high + shift (the generic 32-bit division of
 // i / npix, pix / W costs ~20 instructions each, ~50 of the ~600 a camera-ray warp issues).  Round-up method of

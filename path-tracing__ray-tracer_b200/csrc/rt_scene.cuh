@@ -14,7 +14,7 @@
 namespace b2rt {
 
 #ifndef B2RT_SCAN_UNROLL
-#define B2RT_SCAN_UNROLL 1
+#define B2RT_SCAN_UNROLL 1            // loose planar records per loop trip (box records left few of them)
 #endif
 #ifndef B2RT_BOUNCE_MIN_BLOCKS
 #define B2RT_BOUNCE_MIN_BLOCKS 4      // resident CTAs/SM requested for the float32 planar-scan bounce kernel (64 regs)
@@ -504,7 +504,7 @@ __device__ __forceinline__ bool scan_small(const SceneDev &S, const float4 *sp, 
         if (AnyHit && ok) { if (code_out) *code_out = k; return true; }
     }
 #ifndef B2RT_OPT_SPH
-#define B2RT_OPT_SPH 1
+#define B2RT_OPT_SPH 1             // 0: per-sphere hit_sphere() calls (measurement switch)
 #endif
     if (!B2RT_OPT_SPH) {
         for (int i = 0; i < S.n_sphere; ++i) {
