@@ -150,6 +150,7 @@ int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri,
                     float box_pad, void *d_nodes_out, void *d_top_out, int32_t top_capacity,
                     int32_t *h_meta_out, void *d_temp, size_t temp_bytes, void *stream, int32_t flags);
 /* flags for b2rt_lbvh_build */
+#define B2RT_LBVH_NO_ROTATIONS 2  /* skip the bottom-up tree-rotation pass (measurement switch) */
 #define B2RT_LBVH_RECTS_OUTSIDE 1 /* the rectangles get no place in the hierarchy (set b2rt_scene.bvh_rects_outside too: every
                                      walk then tests them directly first).  For a few room-sized rectangles around a fine
                                      mesh: inside the tree they widen every ancestor box of their leaves. */

@@ -98,7 +98,8 @@ class DeviceScene:
     def __init__(self, packed: PackedScene, precision: int = _lib.P_F32, device=None,
                  top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
                  scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True, ray_sort_min_prims: int = 4096,
-                 scan_boxes: bool = True, surface_records: bool = True, rects_outside: bool = True):
+                 scan_boxes: bool = True, surface_records: bool = True, rects_outside: bool = True,
+                 lbvh_rotations: bool = True):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.packed = packed
@@ -162,7 +163,8 @@ class DeviceScene:
                                                 g_rect.data_ptr(), g_sphere.data_ptr(), g_tri.data_ptr(),
                                                 C.c_float(pad), self.nodes.data_ptr(), self.top.data_ptr(),
                                                 top_nodes, meta, temp.data_ptr(), temp.numel(),
-                                                current_stream_ptr(dev), 1 if self.rects_outside else 0),
+                                                current_stream_ptr(dev),
+                                                (1 if self.rects_outside else 0) | (0 if lbvh_rotations else 2)),
                        "b2rt_lbvh_build")
             self.n_top, self.root, self.n_internal = int(meta[0]), int(meta[1]), int(meta[2])
         s = _lib.SceneStruct()

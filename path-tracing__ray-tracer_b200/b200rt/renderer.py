@@ -101,10 +101,11 @@ class _B200Base(BaseRenderer):
 
     def __init__(self, name: str, precision="f32", device=None, top_nodes: int = 512, scan_max_prims: int = 64,
                  occluder_hints: bool = True, scan_boxes: bool = True, surface_records: bool = True,
-                 rects_outside: bool = True):
+                 rects_outside: bool = True, lbvh_rotations: bool = True):
         super().__init__(name)
         self.surface_records = surface_records
         self.rects_outside = rects_outside
+        self.lbvh_rotations = lbvh_rotations
         self.scan_max_prims = scan_max_prims
         self.occluder_hints = occluder_hints
         self.scan_boxes = scan_boxes
@@ -126,7 +127,8 @@ class _B200Base(BaseRenderer):
         ds = DeviceScene(packed, self.precision, self.device, self.top_nodes, ray_origin_extent=reach,
                          textures_dev=dev_tex, scan_max_prims=self.scan_max_prims,
                          occluder_hints=self.occluder_hints, scan_boxes=self.scan_boxes,
-                         surface_records=self.surface_records, rects_outside=self.rects_outside)
+                         surface_records=self.surface_records, rects_outside=self.rects_outside,
+                         lbvh_rotations=self.lbvh_rotations)
         ds.cam = cam
         ds.h2d_total = ds.h2d_bytes() + self._tex_cache.uploaded_bytes
         return ds
@@ -160,9 +162,10 @@ class B200PathTracer(_B200Base):
                  device=None, top_nodes: int = 512, wave_paths: int = 1 << 26, scan_max_prims: int = 64,
                  fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True, progressive: bool = False,
                  scan_boxes: bool = True, primary_walk: bool = False, surface_records: bool = True,
-                 fused_walk: bool = False, walk_primary: bool = False, rects_outside: bool = True):
+                 fused_walk: bool = False, walk_primary: bool = False, rects_outside: bool = True,
+                 lbvh_rotations: bool = True):
         super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints, scan_boxes,
-                         surface_records, rects_outside)
+                         surface_records, rects_outside, lbvh_rotations)
         self.flags = (0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_walk else 0) | (8 if fused_walk else 0) | (32 if walk_primary else 0)
         # progressive=True: successive render() calls with the same size ADD their samples (global sample
         # indices continue where the last call stopped) instead of discarding the previous frame — the

@@ -220,10 +220,40 @@ __global__ void hierarchy_kernel(int n, const uint32_t *keys, const int *vals, i
     if (i == 0) parent_node[0] = -1;
 }
 
+__device__ __forceinline__ float box_area(const float4 &lo, const float4 &hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+__device__ __forceinline__ void box_union(const float4 &alo, const float4 &ahi, const float4 &blo, const float4 &bhi,
+                                          float4 &lo, float4 &hi) {
+    lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+    hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+}
+__device__ __forceinline__ void write_node(float4 *nodes, int i, const float4 &llo, const float4 &lhi, const float4 &rlo,
+                                           const float4 &rhi, int cl, int cr) {
+    nodes[4 * (size_t)i + 0] = make_float4(llo.x, llo.y, llo.z, lhi.x);
+    nodes[4 * (size_t)i + 1] = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
+    nodes[4 * (size_t)i + 2] = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
+    nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(cl), __int_as_float(cr), 0.f, 0.f);
+}
+// child boxes and references of the (already finished) internal node i, read past the L1
+__device__ __forceinline__ void read_node(const float4 *nodes, int i, float4 &llo, float4 &lhi, float4 &rlo, float4 &rhi,
+                                          int &cl, int &cr) {
+    float4 n0 = __ldcg(nodes + 4 * (size_t)i), n1 = __ldcg(nodes + 4 * (size_t)i + 1),
+           n2 = __ldcg(nodes + 4 * (size_t)i + 2), n3 = __ldcg(nodes + 4 * (size_t)i + 3);
+    llo = make_float4(n0.x, n0.y, n0.z, 0.f); lhi = make_float4(n0.w, n1.x, n1.y, 0.f);
+    rlo = make_float4(n1.z, n1.w, n2.x, 0.f); rhi = make_float4(n2.y, n2.z, n2.w, 0.f);
+    cl = __float_as_int(n3.x); cr = __float_as_int(n3.y);
+}
+
 // Bottom-up refit.  One thread per leaf climbs; the second arrival at a node (atomic flag) owns it.
-__global__ void refit_kernel(int n, const int2 *children, const int *parent_node, const int *parent_leaf,
+// With `rotate`, the owner also tries the four tree rotations of Kensler (2008) — exchange one child with a grandchild
+// on the other side — and applies the one that shrinks the surface area of the re-formed child the most.  Both
+// subtrees are finished and the parent is still waiting on its flag, so the owner is the only thread touching these
+// nodes: one pass, no locks.  (The Morton hierarchy splits space blindly; rotations repair the worst overlaps.)
+__global__ void refit_kernel(int n, int2 *children, const int *parent_node, const int *parent_leaf,
                              const float4 *box_lo, const float4 *box_hi, int *flags, float4 *node_lo, float4 *node_hi,
-                             float4 *nodes) {
+                             float4 *nodes, int rotate) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     int cur = parent_leaf[k];
@@ -236,10 +266,58 @@ __global__ void refit_kernel(int n, const int2 *children, const int *parent_node
         else { llo = __ldcg(node_lo + c.x); lhi = __ldcg(node_hi + c.x); }
         if (c.y < 0) { rlo = box_lo[~c.y]; rhi = box_hi[~c.y]; }
         else { rlo = __ldcg(node_lo + c.y); rhi = __ldcg(node_hi + c.y); }
-        nodes[4 * (size_t)cur + 0] = make_float4(llo.x, llo.y, llo.z, lhi.x);
-        nodes[4 * (size_t)cur + 1] = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
-        nodes[4 * (size_t)cur + 2] = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
-        nodes[4 * (size_t)cur + 3] = make_float4(__int_as_float(c.x), __int_as_float(c.y), 0.f, 0.f);
+        if (rotate) {
+            float best = 0.f;
+            int which = -1;                                   // 0: L<->RL  1: L<->RR  2: R<->LL  3: R<->LR
+            float4 glo[4], ghi[4];                            // grandchild boxes RL, RR, LL, LR
+            int gc[4] = {0, 0, 0, 0};
+            if (c.y >= 0) {
+                read_node(nodes, c.y, glo[0], ghi[0], glo[1], ghi[1], gc[0], gc[1]);
+                const float cur_area = box_area(rlo, rhi);
+                float4 ulo, uhi;
+                box_union(llo, lhi, glo[1], ghi[1], ulo, uhi);
+                float g = cur_area - box_area(ulo, uhi);
+                if (g > best) { best = g; which = 0; }
+                box_union(glo[0], ghi[0], llo, lhi, ulo, uhi);
+                g = cur_area - box_area(ulo, uhi);
+                if (g > best) { best = g; which = 1; }
+            }
+            if (c.x >= 0) {
+                read_node(nodes, c.x, glo[2], ghi[2], glo[3], ghi[3], gc[2], gc[3]);
+                const float cur_area = box_area(llo, lhi);
+                float4 ulo, uhi;
+                box_union(rlo, rhi, glo[3], ghi[3], ulo, uhi);
+                float g = cur_area - box_area(ulo, uhi);
+                if (g > best) { best = g; which = 2; }
+                box_union(glo[2], ghi[2], rlo, rhi, ulo, uhi);
+                g = cur_area - box_area(ulo, uhi);
+                if (g > best) { best = g; which = 3; }
+            }
+            if (which == 0 || which == 1) {                   // L goes below R, a grandchild of R comes up as the new L
+                const int R = c.y, up = which == 0 ? 0 : 1, stay = 1 - up;
+                float4 nlo, nhi;
+                box_union(llo, lhi, glo[stay], ghi[stay], nlo, nhi);
+                if (which == 0) write_node(nodes, R, llo, lhi, glo[1], ghi[1], c.x, gc[1]);
+                else write_node(nodes, R, glo[0], ghi[0], llo, lhi, gc[0], c.x);
+                children[R] = which == 0 ? make_int2(c.x, gc[1]) : make_int2(gc[0], c.x);
+                node_lo[R] = nlo; node_hi[R] = nhi;
+                c.x = gc[up]; llo = glo[up]; lhi = ghi[up];
+                rlo = nlo; rhi = nhi;
+                children[cur] = c;
+            } else if (which == 2 || which == 3) {            // R goes below L, a grandchild of L comes up as the new R
+                const int L = c.x, up = which == 2 ? 2 : 3, stay = 5 - up;
+                float4 nlo, nhi;
+                box_union(rlo, rhi, glo[stay], ghi[stay], nlo, nhi);
+                if (which == 2) write_node(nodes, L, rlo, rhi, glo[3], ghi[3], c.y, gc[3]);
+                else write_node(nodes, L, glo[2], ghi[2], rlo, rhi, gc[2], c.y);
+                children[L] = which == 2 ? make_int2(c.y, gc[3]) : make_int2(gc[2], c.y);
+                node_lo[L] = nlo; node_hi[L] = nhi;
+                c.y = gc[up]; rlo = glo[up]; rhi = ghi[up];
+                llo = nlo; lhi = nhi;
+                children[cur] = c;
+            }
+        }
+        write_node(nodes, cur, llo, lhi, rlo, rhi, c.x, c.y);
         node_lo[cur] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
         node_hi[cur] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
         cur = parent_node[cur];
@@ -387,7 +465,9 @@ cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, 
     if ((e = cub::DeviceRadixSort::SortPairs(base + L.cub, cub_bytes, keys_a, keys_b, vals_a, vals_b, n, 0, 31, stream)))
         return e;
     hierarchy_kernel<<<G, T, 0, stream>>>(n, keys_b, vals_b, children, parent_node, parent_leaf);
-    refit_kernel<<<G, T, 0, stream>>>(n, children, parent_node, parent_leaf, box_lo, box_hi, flags, node_lo, node_hi, nodes);
+    const int rotate = (build_flags & 2) ? 0 : 1;
+    refit_kernel<<<G, T, 0, stream>>>(n, children, parent_node, parent_leaf, box_lo, box_hi, flags, node_lo, node_hi, nodes,
+                                      rotate);
     top_order_kernel<<<1, 1024, 0, stream>>>(n - 1, children, top_capacity, top_id, order, meta);
     finalize_kernel<<<(n - 1 + T - 1) / T, T, 0, stream>>>(n - 1, top_id, meta, nodes, top);
     if ((e = cudaGetLastError())) return e;
