@@ -269,51 +269,54 @@ __global__ void refit_kernel(int n, int2 *children, const int *parent_node, cons
         if (rotate) {
             float best = 0.f;
             int which = -1;                                   // 0: L<->RL  1: L<->RR  2: R<->LL  3: R<->LR
-            float4 glo[4], ghi[4];                            // grandchild boxes RL, RR, LL, LR
-            int gc[4] = {0, 0, 0, 0};
+            float4 RLlo, RLhi, RRlo, RRhi, LLlo, LLhi, LRlo, LRhi;   // grandchild boxes (named: no local-memory arrays)
+            int cRL = 0, cRR = 0, cLL = 0, cLR = 0;
+            float4 ulo, uhi;
             if (c.y >= 0) {
-                read_node(nodes, c.y, glo[0], ghi[0], glo[1], ghi[1], gc[0], gc[1]);
-                const float cur_area = box_area(rlo, rhi);
-                float4 ulo, uhi;
-                box_union(llo, lhi, glo[1], ghi[1], ulo, uhi);
-                float g = cur_area - box_area(ulo, uhi);
+                read_node(nodes, c.y, RLlo, RLhi, RRlo, RRhi, cRL, cRR);
+                const float area = box_area(rlo, rhi);
+                box_union(llo, lhi, RRlo, RRhi, ulo, uhi);
+                float g = area - box_area(ulo, uhi);
                 if (g > best) { best = g; which = 0; }
-                box_union(glo[0], ghi[0], llo, lhi, ulo, uhi);
-                g = cur_area - box_area(ulo, uhi);
+                box_union(RLlo, RLhi, llo, lhi, ulo, uhi);
+                g = area - box_area(ulo, uhi);
                 if (g > best) { best = g; which = 1; }
             }
             if (c.x >= 0) {
-                read_node(nodes, c.x, glo[2], ghi[2], glo[3], ghi[3], gc[2], gc[3]);
-                const float cur_area = box_area(llo, lhi);
-                float4 ulo, uhi;
-                box_union(rlo, rhi, glo[3], ghi[3], ulo, uhi);
-                float g = cur_area - box_area(ulo, uhi);
+                read_node(nodes, c.x, LLlo, LLhi, LRlo, LRhi, cLL, cLR);
+                const float area = box_area(llo, lhi);
+                box_union(rlo, rhi, LRlo, LRhi, ulo, uhi);
+                float g = area - box_area(ulo, uhi);
                 if (g > best) { best = g; which = 2; }
-                box_union(glo[2], ghi[2], rlo, rhi, ulo, uhi);
-                g = cur_area - box_area(ulo, uhi);
+                box_union(LLlo, LLhi, rlo, rhi, ulo, uhi);
+                g = area - box_area(ulo, uhi);
                 if (g > best) { best = g; which = 3; }
             }
-            if (which == 0 || which == 1) {                   // L goes below R, a grandchild of R comes up as the new L
-                const int R = c.y, up = which == 0 ? 0 : 1, stay = 1 - up;
-                float4 nlo, nhi;
-                box_union(llo, lhi, glo[stay], ghi[stay], nlo, nhi);
-                if (which == 0) write_node(nodes, R, llo, lhi, glo[1], ghi[1], c.x, gc[1]);
-                else write_node(nodes, R, glo[0], ghi[0], llo, lhi, gc[0], c.x);
-                children[R] = which == 0 ? make_int2(c.x, gc[1]) : make_int2(gc[0], c.x);
-                node_lo[R] = nlo; node_hi[R] = nhi;
-                c.x = gc[up]; llo = glo[up]; lhi = ghi[up];
-                rlo = nlo; rhi = nhi;
+            if (which == 0 || which == 1) {                   // L goes below R; a grandchild of R comes up as the new L
+                const bool a0 = which == 0;
+                const int R = c.y;
+                const float4 slo = a0 ? RRlo : RLlo, shi = a0 ? RRhi : RLhi;      // the grandchild that stays
+                const float4 plo = a0 ? RLlo : RRlo, phi = a0 ? RLhi : RRhi;      // the one that comes up
+                box_union(llo, lhi, slo, shi, ulo, uhi);
+                if (a0) write_node(nodes, R, llo, lhi, RRlo, RRhi, c.x, cRR);
+                else write_node(nodes, R, RLlo, RLhi, llo, lhi, cRL, c.x);
+                children[R] = a0 ? make_int2(c.x, cRR) : make_int2(cRL, c.x);
+                node_lo[R] = ulo; node_hi[R] = uhi;
+                c.x = a0 ? cRL : cRR; llo = plo; lhi = phi;
+                rlo = ulo; rhi = uhi;
                 children[cur] = c;
-            } else if (which == 2 || which == 3) {            // R goes below L, a grandchild of L comes up as the new R
-                const int L = c.x, up = which == 2 ? 2 : 3, stay = 5 - up;
-                float4 nlo, nhi;
-                box_union(rlo, rhi, glo[stay], ghi[stay], nlo, nhi);
-                if (which == 2) write_node(nodes, L, rlo, rhi, glo[3], ghi[3], c.y, gc[3]);
-                else write_node(nodes, L, glo[2], ghi[2], rlo, rhi, gc[2], c.y);
-                children[L] = which == 2 ? make_int2(c.y, gc[3]) : make_int2(gc[2], c.y);
-                node_lo[L] = nlo; node_hi[L] = nhi;
-                c.y = gc[up]; rlo = glo[up]; rhi = ghi[up];
-                llo = nlo; lhi = nhi;
+            } else if (which == 2 || which == 3) {            // R goes below L; a grandchild of L comes up as the new R
+                const bool a2 = which == 2;
+                const int L = c.x;
+                const float4 slo = a2 ? LRlo : LLlo, shi = a2 ? LRhi : LLhi;
+                const float4 plo = a2 ? LLlo : LRlo, phi = a2 ? LLhi : LRhi;
+                box_union(rlo, rhi, slo, shi, ulo, uhi);
+                if (a2) write_node(nodes, L, rlo, rhi, LRlo, LRhi, c.y, cLR);
+                else write_node(nodes, L, LLlo, LLhi, rlo, rhi, cLL, c.y);
+                children[L] = a2 ? make_int2(c.y, cLR) : make_int2(cLL, c.y);
+                node_lo[L] = ulo; node_hi[L] = uhi;
+                c.y = a2 ? cLL : cLR; rlo = plo; rhi = phi;
+                llo = ulo; lhi = uhi;
                 children[cur] = c;
             }
         }
