@@ -171,8 +171,11 @@ __device__ __forceinline__ bool hit_tri(const SceneDev &S, int i, const Ray<R> &
         int sg = __float_as_int(a) & 0x80000000;
         R Us = __int_as_float(__float_as_int(U) ^ sg), Vs = __int_as_float(__float_as_int(V) ^ sg),
           Ts = __int_as_float(__float_as_int(T) ^ sg);
+        // the range pre-check is a hair wide (2^-20 relative): T <= t_far * |a| in float32 can reject a hit whose divided
+        // distance f * T EQUALS t_far, which the exact tie rule below has to see (coplanar overlapping triangles:
+        // the walk reaches them in tree order, the scan in id order, and both must keep the lowest id)
         bool ok = !(aa < R(1e-6)) && Us >= R(0) && Us <= aa && Vs >= R(0) && Us + Vs <= aa &&
-                  Ts > t_min * aa && Ts <= t_far * aa;
+                  Ts > t_min * aa * R(0.999999) && Ts <= t_far * aa * R(1.000001);
         if (!ok) return false;
         R f = rcp_(a);
         R t = f * T;

@@ -328,3 +328,54 @@ def test_rectangles_outside_the_hierarchy_give_identical_hits():
     x, cx = renderer.B200PathTracer(precision="f32", seed=2, rects_outside=True).render_accum(scene, cam, st)
     y, cy = renderer.B200PathTracer(precision="f32", seed=2, rects_outside=False).render_accum(scene, cam, st)
     assert np.array_equal(x, y) and np.array_equal(cx[:4], cy[:4])
+
+
+@pytest.mark.parametrize("kind", ["coincident", "flat", "coplanar_overlap", "line", "walls_and_spheres"])
+def test_lbvh_builder_degenerate_inputs(kind):
+    """Morton bit allocation, rotations and outside-rectangles on degenerate large inputs: LBVH walk == brute force.
+    coincident: 6 000 copies of one triangle (identical centroids: ties resolved by index bits);
+    flat: a mesh in one plane (zero spread on an axis); coplanar_overlap: overlapping triangles in one plane; line: centroids on a line (zero spread on two axes);
+    walls_and_spheres: 6 000 triangles + 8 room-sized rectangles kept outside the hierarchy + spheres inside it."""
+    rng = np.random.default_rng(4)
+    m = Material(Vec3(0.7, 0.7, 0.7), diffuse=0.8)
+    sc = Scene()
+    n = 6000
+    if kind == "coincident":
+        v = np.tile(np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.2]]), (n, 1))
+    elif kind == "flat":
+        # a regular grid of separated triangles (overlapping coplanar triangles would be exact-t ties, which the
+        # float32 kernels only resolve to the lowest id in scan order — the documented tie cases)
+        gx, gz = np.meshgrid(np.arange(100) * 0.2 - 10, np.arange(60) * 0.33 - 10)
+        c = np.stack([gx.ravel(), np.zeros(n), gz.ravel()], 1)
+        v = (c[:, None, :] + np.array([[0, 0, 0], [0.15, 0, 0], [0, 0, 0.25]])[None]).reshape(-1, 3)
+    elif kind == "coplanar_overlap":
+        # random OVERLAPPING triangles in one plane: rays hit several of them at float-equal distances, and the
+        # walk (tree order) must keep the same lowest id as the scan (id order)
+        c = np.stack([rng.uniform(-10, 10, n), np.zeros(n), rng.uniform(-10, 10, n)], 1)
+        v = (c[:, None, :] + np.array([[0, 0, 0], [0.3, 0, 0], [0, 0, 0.3]])[None]).reshape(-1, 3)
+    elif kind == "line":
+        c = np.stack([np.linspace(-10, 10, n), np.zeros(n), np.zeros(n)], 1)
+        v = (c[:, None, :] + np.array([[0, -0.5, -0.5], [0, 0.5, -0.5], [0, 0.0, 0.5]])[None]).reshape(-1, 3)
+    else:
+        c = rng.uniform(-8, 8, (n, 3))
+        v = (c[:, None, :] + rng.normal(scale=0.2, size=(n, 3, 3))).reshape(-1, 3)
+        for k in range(8):
+            a = rng.uniform(-12, -10, 3)
+            sc.add_object(Plane(Vec3(*a), Vec3(0, 1, 0), Vec3(1, 0, 0), Vec3(0, 0, 1), 22.0 + k, 21.0, m))
+        for k in range(5):
+            sc.add_object(Sphere(Vec3(*rng.uniform(-6, 6, 3)), 0.7, m))
+    sc.objects.append(packer.TriangleMesh(v, np.arange(3 * n).reshape(-1, 3), m))
+    pk = packer.pack_scene(sc, "numba")
+    q = 20000
+    o = rng.uniform(-12, 12, (q, 3))
+    d = rng.normal(size=(q, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    if kind in ("coincident", "line"):
+        d = (rng.uniform(-0.5, 0.5, (q, 3)) + [0.3, 0.3, 0.0]) - o * [0 if kind == "line" else 1, 1, 1]      # aim at the geometry
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+    a_ids, a_rec = renderer.trace_rays(sc, o, d, "numba", "f32", use_bvh=True, packed=pk)
+    b_ids, b_rec = renderer.trace_rays(sc, o, d, "numba", "f32", use_bvh=False, packed=pk)
+    assert np.array_equal(a_ids, b_ids)
+    assert np.array_equal(a_rec[:, 0], b_rec[:, 0])
+    assert (b_ids >= 0).mean() > 0.02
+    occ, _ = renderer.trace_rays(sc, o, d, "numba", "f32", use_bvh=True, any_hit=True, packed=pk)
+    assert np.array_equal(occ >= 0, b_ids >= 0)
