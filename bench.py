@@ -44,6 +44,17 @@ STEP_BYTES_PER_PATH = 550.0     # whole-wavefront queue traffic per path (SURVEY
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 13.075816e9 / 8
 
 
+# stdout carries exactly ONE line, the JSON result: everything else that libraries print to file descriptor 1 (NCCL's
+# "NCCL version ..." banner at NCCL_DEBUG=WARN/VERSION, numba, ...) is sent to stderr by pointing fd 1 at fd 2 for the
+# whole run and writing the result to the saved descriptor.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+
+
 def build_scene():
     from b200rt.cornell import CustomSceneBuilder
     random.seed(0)
@@ -145,7 +156,7 @@ def run_reference_arm(args):
     paths = w * h * spp * args.steps
     v = paths / dt / 1e6
     sample = f"each step = {w}x{h} x {spp} spp of the workload ({w * h * spp} paths)"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -186,8 +197,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200RT_NCCL_DEBUG", "WARN")
         td.init_process_group("nccl", device_id=dev)
     spp = args.spp
     scene, camera = build_scene()
@@ -317,7 +326,7 @@ def main():
         }
         if spp != SPP:
             out["invalid"] = f"debug run at {spp} spp (the headline config is {SPP})"
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         td.destroy_process_group()
 
