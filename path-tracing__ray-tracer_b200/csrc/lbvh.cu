@@ -72,6 +72,7 @@ __global__ void bounds_kernel(int n, int n_rect, int n_sphere, const float4 *rec
                               double *moments, int n_outside) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float c[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};   // centroid bounds
+    float ext[3] = {0.f, 0.f, 0.f};                          // box extent of this primitive
     const bool outside = i < n_outside;                      // kept out of the hierarchy (see lbvh_build)
     if (outside) {
         // a far-away point box no ray reaches; its 31-bit key sorts it behind every real primitive, so the root
@@ -84,6 +85,7 @@ __global__ void bounds_kernel(int n, int n_rect, int n_sphere, const float4 *rec
         c[0] = c[3] = 0.5f * (b.lo.x + b.hi.x);
         c[1] = c[4] = 0.5f * (b.lo.y + b.hi.y);
         c[2] = c[5] = 0.5f * (b.lo.z + b.hi.z);
+        ext[0] = b.hi.x - b.lo.x; ext[1] = b.hi.y - b.lo.y; ext[2] = b.hi.z - b.lo.z;
     }
     typedef cub::BlockReduce<float, 256> BR;
     __shared__ typename BR::TempStorage tmp;
@@ -95,40 +97,50 @@ __global__ void bounds_kernel(int n, int n_rect, int n_sphere, const float4 *rec
             else atomicMax(scene_bounds + k, float_to_ordered(r));
         }
     }
-    // first and second moments of the centroids: the Morton bit allocation follows their spread per axis
-    for (int k = 0; k < 6; ++k) {
-        float v = (i < n && !outside) ? (k < 3 ? c[k] : c[k - 3] * c[k - 3]) : 0.f;
+    // first and second moments of the centroids and the summed box extents: the Morton bit allocation follows the
+    // number of primitives that fit across the scene along each axis
+    for (int k = 0; k < 9; ++k) {
+        float v = (i < n && !outside) ? (k < 3 ? c[k] : k < 6 ? c[k - 3] * c[k - 3] : ext[k - 6]) : 0.f;
         float r = BR(tmp).Sum(v);
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(moments + k, (double)r);
     }
 }
 
-// Morton bits per axis (sum 30).  Equal spreads give the classic 10/10/10.  An axis along which the centroids
-// spread less gets fewer bits: b_k = 10 + log2(sigma_k / geometric mean sigma), and the interleave below always
-// takes the next bit from the axis with the most bits left, so the flat axis is split LATE.  For 2.5-D data (a
-// terrain, a city) the classic x,y,z cycle spends every third split on the flat axis; those splits cut the mesh
-// into height bands whose boxes overlap in the other two axes.  Measured on the 1 M-triangle height field:
-// 10/10/10 168.6 ms per step, 11/8/11 (this rule) 132.7, 12/6/12 130.5, 15/0/15 136.8.
-__device__ __forceinline__ void morton_bits(int n, const double *moments, int *bits) {
-    float sig[3], mx = 0.f;
+// Morton bits per axis (sum 30) and the world-space spread the cells are measured in.
+// Two facts bound the useful splits along an axis: (1) cells should stay roughly CUBIC in world space (the surface-area
+// heuristic), so the next bit goes to the axis whose cell is currently the longest (spread_k / 2^bits_k, spread = 4 sigma
+// of the centroids); (2) key bits finer than the primitives cannot separate them any more, so an axis stops at
+// cap_k = log2(spread_k / mean primitive extent_k) + 1 bits.  Equal spreads and extents give the classic 10/10/10.
+// On 2.5-D data (a terrain, a city) the classic x,y,z cycle spends every third split on the flat axis and cuts the mesh
+// into bands whose boxes overlap in the other two axes.  Measured on the 1 M-triangle height field (rough: triangles
+// of 0.03 x 0.85 x 0.06), ms per step with three rotation sweeps: 10/10/10 194.9, 11/8/11 110.1, 12/7/11 98.2,
+// 14/4/12 97.0, 12/6/12 90.5, 13/4/13 88.4; this rule: 91.0.
+__device__ __forceinline__ void morton_bits(int n, const double *moments, int *bits, float *spread) {
+    float cap[3];
+    bool any = false;
     for (int k = 0; k < 3; ++k) {
-        double m = moments[k] / n, v = moments[3 + k] / n - m * m;
-        sig[k] = sqrtf(fmaxf((float)v, 0.f));
-        mx = fmaxf(mx, sig[k]);
+        const double m = moments[k] / n, v = moments[3 + k] / n - m * m;
+        const float ext = (float)(moments[6 + k] / n);
+        spread[k] = 4.f * sqrtf(fmaxf((float)v, 0.f));
+        cap[k] = spread[k] > 0.f ? fminf(fmaxf(log2f(spread[k] / fmaxf(ext, 1e-30f)) + 1.f, 0.f), 20.f) : 0.f;
+        any = any || cap[k] >= 1.f;
+        bits[k] = 0;
     }
-    float L[3], mean = 0.f;
-    for (int k = 0; k < 3; ++k) { L[k] = log2f(fmaxf(sig[k], 1e-4f * mx + 1e-30f)); mean += L[k] / 3.f; }
-    int sum = 0;
-    for (int k = 0; k < 3; ++k) { bits[k] = min(14, max(2, (int)lrintf(10.f + L[k] - mean))); sum += bits[k]; }
-    while (sum > 30) {                                       // take from the axis with the most bits
-        int a = bits[0] >= bits[1] ? (bits[0] >= bits[2] ? 0 : 2) : (bits[1] >= bits[2] ? 1 : 2);
-        --bits[a]; --sum;
-    }
-    while (sum < 30) {                                       // give to the widest-spread axis that still has room
+    if (!any) { bits[0] = bits[1] = bits[2] = 10; spread[0] = spread[1] = spread[2] = 1.f; return; }
+    for (int t = 0; t < 30; ++t) {
         int a = -1;
-        for (int k = 0; k < 3; ++k) if (bits[k] < 14 && (a < 0 || L[k] > L[a])) a = k;
-        ++bits[a]; ++sum;
+        float best = -1.f;
+        for (int k = 0; k < 3; ++k) {                        // longest cell among the axes that still have room
+            const float cell = spread[k] / (float)(1u << bits[k]);
+            if ((float)bits[k] + 1.f <= cap[k] && cell > best) { best = cell; a = k; }
+        }
+        if (a < 0) {                                         // every axis at its cap: the remaining bits only break ties
+            best = -1e30f;                                   // between primitives; they go where the cap is exceeded least
+            for (int k = 0; k < 3; ++k)
+                if (bits[k] < 20 && cap[k] - (float)bits[k] > best) { best = cap[k] - (float)bits[k]; a = k; }
+        }
+        ++bits[a];
     }
 }
 
@@ -154,9 +166,10 @@ __global__ void morton_kernel(int n, const float4 *box_lo, const float4 *box_hi,
     float cx = (0.5f * (a.x + b.x) - lo[0]) / ext[0];
     float cy = (0.5f * (a.y + b.y) - lo[1]) / ext[1];
     float cz = (0.5f * (a.z + b.z) - lo[2]) / ext[2];
-    if (bx <= 0) {                                           // automatic allocation from the centroid spread
+    float spread[3] = {1.f, 1.f, 1.f};
+    if (bx <= 0) {                                           // automatic allocation (morton_bits)
         int bits[3];
-        morton_bits(n - n_outside, moments, bits);
+        morton_bits(n - n_outside, moments, bits, spread);
         bx = bits[0]; by = bits[1]; bz = bits[2];
     }
     if (bx == 10 && by == 10 && bz == 10) {
@@ -167,6 +180,7 @@ __global__ void morton_kernel(int n, const float4 *box_lo, const float4 *box_hi,
     } else {
         // uneven bit allocation (bx + by + bz <= 30): interleave from the top, always taking the next bit of the
         // axis that has the most bits left (ties x, y, z), so every axis reaches its last bit at the bottom
+        // (taking it from the axis whose world-space cell is currently the longest instead measured 118 vs 91 ms)
         int rem[3] = {bx, by, bz};
         const float c[3] = {cx, cy, cz};
         uint32_t q[3];
@@ -418,7 +432,7 @@ TempLayout layout(int n) {
     L.children = take(8 * m); L.parent_node = take(4 * m); L.parent_leaf = take(4 * (size_t)n);
     L.flags = take(4 * m); L.node_lo = take(16 * m); L.node_hi = take(16 * m);
     L.top_id = take(4 * m); L.order = take(4 * 4096); L.bounds = take(32); L.meta = take(32);
-    L.moments = take(64);
+    L.moments = take(96);
     L.pos_of = take(4 * (size_t)n);
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
@@ -467,7 +481,7 @@ cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, 
     if ((e = cudaMemsetAsync(flags, 0, 4 * (size_t)(n - 1), stream))) return e;
     if ((e = cudaMemsetAsync(top_id, 0xff, 4 * (size_t)(n - 1), stream))) return e;
     if ((e = cudaMemsetAsync(meta, 0, 32, stream))) return e;
-    if ((e = cudaMemsetAsync(moments, 0, 64, stream))) return e;
+    if ((e = cudaMemsetAsync(moments, 0, 96, stream))) return e;
     bounds_kernel<<<G, T, 0, stream>>>(n, n_rect, n_sphere, rect, sphere, tri, pad, box_lo, box_hi, bounds, moments, n_outside);
     int mb[3] = {0, 0, 0};                                   // 0: automatic (morton_bits)
     if (const char *ev = getenv("B2RT_MORTON_BITS")) {       // measurement hook: "10,10,10" forces an allocation
