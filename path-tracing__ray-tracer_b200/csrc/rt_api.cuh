@@ -175,6 +175,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         PrimaryArgs<R> PA;
         PA.cam = c; PA.W = W; PA.H = H; PA.spp_wave = k; PA.first_sample = a.sample_offset + done; PA.seed = a.seed;
         PA.by_npix = FastDiv::make((unsigned)npix); PA.by_w = FastDiv::make((unsigned)W);
+        PA.tiles_x = (W % 8 == 0 && H % 4 == 0) ? W / 8 : 0;
+        PA.by_tiles = FastDiv::make((unsigned)(PA.tiles_x > 0 ? PA.tiles_x : 1));
         if ((e = cudaMemsetAsync(counts, 0, counts_bytes, st))) return e;
         if (!fuse_primary) {
             prof_begin(kRaygen, st);
