@@ -47,12 +47,21 @@ NCU_TRAFFIC_BYTES_PER_LAUNCH = 13.075816e9 / 8
 # stdout carries exactly ONE line, the JSON result: everything else that libraries print to file descriptor 1 (NCCL's
 # "NCCL version ..." banner at NCCL_DEBUG=WARN/VERSION, numba, ...) is sent to stderr by pointing fd 1 at fd 2 for the
 # whole run and writing the result to the saved descriptor.
-_RESULT_FD = os.dup(1)
-os.dup2(2, 1)
+_RESULT_FD = None
+
+
+def claim_stdout() -> None:
+    """Called first thing in main(): from here on fd 1 is stderr, the result line goes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(obj) -> None:
-    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
 
 
 def build_scene():
@@ -177,6 +186,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
