@@ -417,8 +417,26 @@ class Scene:
     def add_object(self, obj: Hittable):
         self.objects.append(obj)
 
+    def add_mesh(self, vertices, faces, material, uvs=None):
+        """Bulk triangle ingestion: one ``packer.TriangleMesh`` entry in ``objects`` that the packer
+        expands, vectorised, into ``len(faces)`` triangles — the object-per-triangle API (``add_object(Triangle(..))``,
+        ``core/scene.py:35-36``) cannot express million-triangle scenes in reasonable time.  Returns the mesh."""
+        from .packer import TriangleMesh
+        mesh = TriangleMesh(vertices, faces, material, uvs)
+        self.objects.append(mesh)
+        return mesh
+
+    def add_obj(self, path: str, material, scale: float = 1.0, translate=(0.0, 0.0, 0.0)):
+        """``add_mesh`` from a Wavefront OBJ file (``packer.load_obj``)."""
+        from .packer import load_obj
+        mesh = load_obj(path, material, scale, translate)
+        self.objects.append(mesh)
+        return mesh
+
     def build_bvh(self):
-        if self.objects:
+        # the host-side BVH mirrors the reference's (it shuffles ``objects``); bulk meshes only exist on the device
+        prims = [o for o in self.objects if hasattr(o, "bounding_box")]
+        if prims and len(prims) == len(self.objects):
             self.bvh_root = BVHNode(self.objects, 0, len(self.objects))
 
     def add_light_sample(self, pos: Vec3):

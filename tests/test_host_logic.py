@@ -354,3 +354,25 @@ def test_surface_records_and_bounds(cornell):
     from b200rt.scene_api import Scene
     elo, ehi = packer.pack_scene(Scene(), "numba").bounds()
     assert (elo > ehi).all()                         # empty scene: "unknown"
+
+
+def test_scene_add_mesh_and_add_obj(tmp_path):
+    """Bulk mesh ingestion through the Scene mirror: add_mesh / add_obj put one TriangleMesh into scene.objects and the
+    packer expands it; build_bvh() leaves such scenes to the device builder."""
+    from b200rt import packer
+    from b200rt.scene_api import Material, Plane, Scene, Vec3
+    sc = Scene()
+    m = Material(Vec3(0.5, 0.6, 0.7), diffuse=0.8)
+    sc.add_object(Plane(Vec3(-1, 0, -1), Vec3(0, 1, 0), Vec3(1, 0, 0), Vec3(0, 0, 1), 2.0, 2.0, m))
+    v = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], dtype=float)
+    mesh = sc.add_mesh(v, [[0, 1, 2], [0, 2, 3]], m, uvs=[[0, 0], [1, 0], [1, 1], [0, 1]])
+    obj = tmp_path / "tri.obj"
+    obj.write_text("v 0 0 1\nv 1 0 1\nv 0 1 1\nf 1 2 3\n")
+    sc.add_obj(str(obj), m, scale=2.0)
+    sc.build_bvh()
+    assert sc.bvh_root is None and len(sc.objects) == 3 and sc.objects[1] is mesh
+    pk = packer.pack_scene(sc, "numba")
+    assert (pk.n_rect, pk.n_sphere, pk.n_tri) == (1, 0, 3)
+    T = pk.tri.reshape(-1, 3, 4)
+    assert np.allclose(T[2, 0, :3], [0, 0, 2]) and np.allclose(T[2, 1, :3], [2, 0, 0])       # scaled OBJ triangle
+    assert pk.order[1].tolist() == [1, 0] and pk.order[3].tolist() == [2, 0]                  # (object index, face index)
