@@ -48,32 +48,62 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
-    """``defines``/``out`` build an experimental variant (e.g. ("-DB2RT_SCAN_UNROLL=2",)) next to the default."""
+    """``defines``/``out`` build an experimental variant (e.g. ("-DB2RT_SCAN_UNROLL=2",)) next to the default.
+
+    Safe under ``torchrun``: an exclusive ``fcntl`` lock serialises the ranks, the ones that waited re-check
+    staleness under the lock (so only the first compiles), objects and the library are written to temporary
+    names and moved into place with ``os.replace`` so no process can ``dlopen`` a half-written file."""
+    import fcntl
     lib_path = out or LIB_PATH
     if not force and not defines and not is_stale():
         return LIB_PATH
-    tag = "" if not defines else "_" + "_".join(d.replace("-D", "").replace("=", "") for d in defines)
     os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not defines and not is_stale():      # another rank built it while this one waited
+                return LIB_PATH
+            return _build_locked(verbose, tuple(defines), lib_path)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool, defines: tuple, lib_path: str) -> str:
+    tag = "" if not defines else "_" + "_".join(d.replace("-D", "").replace("=", "") for d in defines)
     exe = nvcc()
+    pid = os.getpid()
     objs, procs = [], []
     for src, extra in UNITS:
         obj = os.path.join(BUILD, src.replace(".cu", tag + ".o"))
-        cmd = [exe, *ARCH, *COMMON, *extra, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
+        tmp = f"{obj}.{pid}.tmp"
+        cmd = [exe, *ARCH, *COMMON, *extra, *defines, "-c", os.path.join(CSRC, src), "-o", tmp]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((src, tmp, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
-    for src, p in procs:
+    failed = None
+    for src, tmp, obj, p in procs:
         log, _ = p.communicate()
         if verbose and log:
             print(log)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{log}")
-    link = [exe, *ARCH, "-shared", "-o", lib_path, *objs, "-lcudart"]
+            failed = failed or f"nvcc failed on {src}:\n{log}"
+        else:
+            os.replace(tmp, obj)
+    if failed:
+        for _, tmp, _, _ in procs:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+        raise RuntimeError(failed)
+    tmp_lib = f"{lib_path}.{pid}.tmp"
+    link = [exe, *ARCH, "-shared", "-o", tmp_lib, *objs, "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp_lib):
+            os.remove(tmp_lib)
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_lib, lib_path)
     return lib_path
 
 

@@ -33,6 +33,13 @@ def _torch_real(precision: int):
     return torch.float64 if precision == _lib.P_F64 else torch.float32
 
 
+def _fingerprint(pixels) -> int:
+    import zlib
+    a = np.asarray(pixels).reshape(-1)
+    step = max(1, a.size // 65536)
+    return zlib.crc32(np.ascontiguousarray(a[::step]).tobytes()) ^ (a.size & 0xFFFFFFFF)
+
+
 class _TextureCache:
     """Device copies of the textures as RGBX8 (one 32-bit load per texel).
 
@@ -53,6 +60,10 @@ class _TextureCache:
         self._info = None
         self.uploaded_bytes = 0
 
+    def invalidate(self) -> None:
+        """Forget both cache levels (call after editing ``Texture.pixels`` in place)."""
+        self._key = self._pin_key = None
+
     def get(self, scene, device):
         from .packer import texture_paths_sorted
         texs = {}
@@ -61,7 +72,11 @@ class _TextureCache:
             if t is not None and getattr(t, "path", None):
                 texs.setdefault(t.path, t)
         paths = texture_paths_sorted(scene)
-        pin_key = tuple((p, id(texs[p].pixels), texs[p].pixels.shape) for p in paths)
+        # identity + shape + a strided content fingerprint (<= 64 Ki samples per texture): in-place edits and a freed
+        # array whose id() is reused by a new array of the same shape are caught without re-reading 52 MB per call
+        # (the reference re-reads its textures on every render(), cuda_path_tracer.py:901-932).  invalidate() forces
+        # a full re-read after an edit the fingerprint could miss (a single changed texel between two samples).
+        pin_key = tuple((p, id(texs[p].pixels), texs[p].pixels.shape, _fingerprint(texs[p].pixels)) for p in paths)
         key = (pin_key, str(device))
         if self.enabled and key == self._key:
             self.uploaded_bytes = 0
@@ -192,8 +207,14 @@ class B200PathTracer(_B200Base):
         rank, world = dist.rank_world()
         spp_local, offset = dist.split_samples(spp, rank, world)
         done = 0
-        if self.progressive and self._prog is not None and self._prog["size"] == (W, H):
-            done = self._prog["spp"]
+        if self.progressive:
+            # the running sums belong to ONE image: another scene object, camera, size or depth starts a new one
+            # (reset() does the same explicitly, e.g. after editing the scene in place)
+            key = (id(scene), tuple(float(x) for x in ds.cam), W, H, depth)
+            if self._prog is not None and self._prog["key"] != key:
+                self._prog = None
+            if self._prog is not None:
+                done = self._prog["spp"]
         offset += done                              # this call's samples follow the ones already accumulated
         wave = self.spp_per_wave or max(1, min(max(spp_local, 1), self.wave_paths // max(1, W * H)))
         wave = max(1, min(wave, max(spp_local, 1)))
@@ -213,17 +234,25 @@ class B200PathTracer(_B200Base):
                   u8=torch.empty(W * H * 3, dtype=torch.uint8, device=self.device),
                   cam=_lib.dbl_array(ds.cam))
         st["spp_done_before"] = done
+        st["prog_key"] = (id(scene), tuple(float(x) for x in ds.cam), W, H, depth)
         return st
 
     def _fold_progressive(self, st: dict) -> None:
         """progressive mode: add this call's (already reduced) sums to the running total and resolve that."""
         if not self.progressive:
             return
-        size = (st["W"], st["H"])
-        if self._prog is None or self._prog["size"] != size:
-            self._prog = dict(size=size, accum=torch.zeros_like(st["accum"]), spp=0)
+        if self._prog is None or self._prog["key"] != st["prog_key"]:
+            self._prog = dict(key=st["prog_key"], accum=torch.zeros_like(st["accum"]), accum_sq=None, spp=0)
         self._prog["accum"] += st["accum"]
         self._prog["spp"] += st["spp"]
+        if st["accum_sq"] is not None:              # the sums of squares continue with the sums
+            if self._prog["accum_sq"] is None:
+                if self._prog["spp"] != st["spp"]:
+                    raise RuntimeError("progressive render_accum(want_sumsq=True) must ask for the sums of squares "
+                                       "from the first call on (or call reset())")
+                self._prog["accum_sq"] = torch.zeros_like(st["accum_sq"])
+            self._prog["accum_sq"] += st["accum_sq"]
+            st["accum_sq"] = self._prog["accum_sq"]
         st["accum"], st["spp"] = self._prog["accum"], self._prog["spp"]
 
     def reset(self) -> None:

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/b200rt.h"
@@ -29,28 +30,51 @@ inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 using b2rt::Api;
 
 // ---- per-kernel-class event timing ----------------------------------------------------------------
+// State is per DEVICE (events belong to the device they were created on) and guarded by a mutex: host threads that
+// drive different GPUs, or the same GPU, never share a vector unsynchronised.  Records are bounded.
 namespace b2rt {
 namespace {
 struct ProfRec { int cls; cudaEvent_t a, b; };
-bool g_prof_on = false;
-std::vector<ProfRec> g_prof_recs;
-std::vector<cudaEvent_t> g_prof_pool;
-cudaEvent_t prof_event() {
+struct ProfState {
+    std::mutex mu;
+    bool on = false, open = false;          // open: the last record still waits for its end event
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+};
+constexpr int kMaxDevices = 64;
+constexpr size_t kMaxProfRecs = size_t(1) << 20;      // ~90 frames of the headline bench; further launches are not recorded
+ProfState g_prof[kMaxDevices];
+ProfState *prof_state() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    return &g_prof[dev];
+}
+cudaEvent_t prof_event(ProfState &p) {
     cudaEvent_t e;
-    if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    if (!p.pool.empty()) { e = p.pool.back(); p.pool.pop_back(); }
     else cudaEventCreate(&e);
     return e;
 }
 }  // namespace
 void prof_begin(int cls, cudaStream_t st) {
-    if (!g_prof_on) return;
-    ProfRec r{cls, prof_event(), prof_event()};
+    ProfState *p = prof_state();
+    if (!p || !p->on) return;
+    std::lock_guard<std::mutex> lock(p->mu);
+    p->open = false;
+    if (p->recs.size() >= kMaxProfRecs) return;
+    ProfRec r{cls, prof_event(*p), prof_event(*p)};
     cudaEventRecord(r.a, st);
-    g_prof_recs.push_back(r);
+    cudaEventRecord(r.b, st);          // re-recorded by prof_end; never left unrecorded
+    p->recs.push_back(r);
+    p->open = true;
 }
 void prof_end(cudaStream_t st) {
-    if (!g_prof_on || g_prof_recs.empty()) return;
-    cudaEventRecord(g_prof_recs.back().b, st);
+    ProfState *p = prof_state();
+    if (!p || !p->on) return;
+    std::lock_guard<std::mutex> lock(p->mu);
+    if (!p->open || p->recs.empty()) return;
+    cudaEventRecord(p->recs.back().b, st);
+    p->open = false;
 }
 }  // namespace b2rt
 
@@ -185,23 +209,29 @@ int b2rt_resolve(int32_t precision, const void *d_accum, int32_t width, int32_t 
 }
 
 int b2rt_profile_enable(int32_t on) {
-    b2rt::g_prof_on = on != 0;
+    b2rt::ProfState *p = b2rt::prof_state();
+    if (!p) return fail_msg("b2rt_profile_enable: no current device");
+    std::lock_guard<std::mutex> lock(p->mu);
+    p->on = on != 0;
     return 0;
 }
 
 int b2rt_profile_read(double *h_ms, int64_t *h_launches) {
     for (int k = 0; k < b2rt::kNumClasses; ++k) { h_ms[k] = 0.0; h_launches[k] = 0; }
-    for (auto &r : b2rt::g_prof_recs) {
+    b2rt::ProfState *p = b2rt::prof_state();
+    if (!p) return fail_msg("b2rt_profile_read: no current device");
+    std::lock_guard<std::mutex> lock(p->mu);
+    for (auto &r : p->recs) {
         cudaError_t e = cudaEventSynchronize(r.b);
         if (e) return fail("b2rt_profile_read", e);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.a, r.b);
         h_ms[r.cls] += ms;
         h_launches[r.cls] += 1;
-        b2rt::g_prof_pool.push_back(r.a);
-        b2rt::g_prof_pool.push_back(r.b);
+        p->pool.push_back(r.a);
+        p->pool.push_back(r.b);
     }
-    b2rt::g_prof_recs.clear();
+    p->recs.clear();
     return 0;
 }
 

@@ -13,13 +13,25 @@ namespace b2rt {
 
 inline size_t smem_top_bytes(const SceneDev &S) { return (size_t)S.n_top * 64; }
 
-inline int persistent_grid(const void *kernel, int block, size_t smem) {
+// Dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel (top levels: up to kTopMax * 64 B,
+// MODE 6 adds the scan and surface records on top).  Returns an error when the request exceeds the device limit.
+inline cudaError_t opt_in_smem(const void *kernel, size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+// persistent grid = resident CTAs per SM x SM count (a multiple of the 148 SMs); a kernel that cannot be resident
+// at all (occupancy 0: too much shared memory or registers for the block size) is an error, not a grid of 1 per SM
+inline cudaError_t persistent_grid(const void *kernel, int block, size_t smem, int *grid) {
     int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
-    if (per_sm < 1) per_sm = 1;
-    return sms * per_sm;
+    cudaError_t e;
+    if ((e = opt_in_smem(kernel, smem))) return e;
+    if ((e = cudaGetDevice(&dev))) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev))) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem))) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    *grid = sms * per_sm;
+    return cudaSuccess;
 }
 
 template <typename R>
@@ -28,6 +40,8 @@ cudaError_t Api<R>::primary_hits(const b2rt_scene *s, const double *cam, int W, 
     SceneDev S = make_scene_dev(s);
     Cam<R> c = make_cam<R>(cam);
     int n = W * H, T = 128;
+    if (cudaError_t e = opt_in_smem((const void *)primary_hits_kernel<R, true>, smem_top_bytes(S))) return e;
+    if (cudaError_t e = opt_in_smem((const void *)primary_hits_kernel<R, false>, smem_top_bytes(S))) return e;
     if (S.semantics == B2RT_SEM_CPU)
         primary_hits_kernel<R, true><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, R(du), R(dv), R(t_min), R(t_max), use_bvh, ids, tt);
     else
@@ -42,6 +56,8 @@ cudaError_t Api<R>::trace_rays(const b2rt_scene *s, int n, const double *o, cons
     int T = 128;
     if (n <= 0) return cudaSuccess;
     const size_t sm = use_bvh == 2 ? smem_scan_bytes(S) + 64 : smem_top_bytes(S);
+    if (cudaError_t e = opt_in_smem((const void *)trace_rays_kernel<R, true>, sm)) return e;
+    if (cudaError_t e = opt_in_smem((const void *)trace_rays_kernel<R, false>, sm)) return e;
     if (S.semantics == B2RT_SEM_CPU)
         trace_rays_kernel<R, true><<<(n + T - 1) / T, T, sm, st>>>(S, n, o, d, R(t_min), R(t_max), any_hit, use_bvh, ids, rec);
     else
@@ -58,6 +74,7 @@ cudaError_t Api<R>::whitted_cpu(const b2rt_scene *s, const double *cam, int W, i
     V3<R> amb = {R(ambient[0]), R(ambient[1]), R(ambient[2])};
     V3<R> lc = {R(light_color[0]), R(light_color[1]), R(light_color[2])};
     int n = W * H, T = 128;
+    if (cudaError_t e = opt_in_smem((const void *)whitted_cpu_kernel<R>, smem_top_bytes(S))) return e;
     whitted_cpu_kernel<R><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, jitter, max_depth, amb, lc, rgb);
     return cudaGetLastError();
 }
@@ -70,6 +87,7 @@ cudaError_t Api<R>::whitted_texture(const b2rt_scene *s, const double *cam, int 
     int n = W * H, T = 128;
     if (sizeof(R) == 4 && S.scan_incoherent && S.n_scan > 0 && S.surf)
         whitted_texture_kernel<R, true><<<(n + T - 1) / T, T, smem_scan_bytes(S) + smem_surf_bytes(S), st>>>(S, c, W, H, spp, max_depth, rgb, u8);
+    else if (cudaError_t e = opt_in_smem((const void *)whitted_texture_kernel<R, false>, smem_top_bytes(S))) return e;
     else
         whitted_texture_kernel<R, false><<<(n + T - 1) / T, T, smem_top_bytes(S), st>>>(S, c, W, H, spp, max_depth, rgb, u8);
     return cudaGetLastError();
@@ -142,37 +160,43 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     const size_t smem_shadow = S.scan_incoherent ? smem_scan_only : smem;
     const size_t smem_scan = smem_scan_only + smem_surf_bytes(S);           // bounce kernels also stage the surface records
     const int T = 256;
-    static int g_extend = 0, g_shade = 0, g_shadow = 0, g_simple = 0;
+    cudaError_t e;
     // persistent grids: resident CTAs per SM x SM count (a multiple of the 148 SMs)
-    g_extend = persistent_grid((const void *)extend_kernel<R>, T, smem);
-    g_shade = persistent_grid((const void *)shade_kernel<R, Rng, 0>, T, 0);
+    int g_extend = 0, g_shade = 0, g_shadow = 0, g_simple = 0, g_fuse_bvh = 0, g_fuse_scan = 0, g_walk = 0;
+    int g_primary = 0, g_primary_small = 0, g_primary_scan = 0;
     const bool fused = !(a.flags & 1);
     const size_t smem_bvh = smem;                                           // MODE 1 / 4: generic streams only
     const size_t smem_bvh_small = smem + smem_scan;                         // MODE 6: + scan and surface records
-    const int g_fuse_bvh = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem_bvh);
     const bool planar = sizeof(R) == 4 && S.n_scan > 0 && S.surf != nullptr;
-    const int g_fuse_scan = planar ? persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_scan)
-                                   : persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, 0);
-    g_shadow = persistent_grid((const void *)shadow_kernel<R>, T, smem_shadow);
+    // MODE 2 (generic scan) stages the scan records only when it uses them: for the occluder hints of float32 scenes
+    const size_t smem_generic = (sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && S.occl_hint) ? smem_scan_only : 0;
+    if ((e = persistent_grid((const void *)extend_kernel<R>, T, smem, &g_extend))) return e;
+    if ((e = persistent_grid((const void *)shade_kernel<R, Rng, 0>, T, 0, &g_shade))) return e;
+    if ((e = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem_bvh, &g_fuse_bvh))) return e;
+    if (planar) e = persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_scan, &g_fuse_scan);
+    else e = persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, smem_generic, &g_fuse_scan);
+    if (e) return e;
+    if ((e = persistent_grid((const void *)shadow_kernel<R>, T, smem_shadow, &g_shadow))) return e;
     // large scenes: incoherent bounces run the persistent walk kernel + the wavefront shade stage
     const bool walk_kernel = fused && sizeof(R) == 4 && !S.scan_incoherent && !(a.flags & 8);
-    const int g_walk = persistent_grid((const void *)extend_walk_kernel<R>, T, smem);
-    g_simple = persistent_grid((const void *)accumulate_kernel<R>, T, 0);
+    if ((e = persistent_grid((const void *)extend_walk_kernel<R>, T, smem, &g_walk))) return e;
+    if ((e = persistent_grid((const void *)accumulate_kernel<R>, T, 0, &g_simple))) return e;
 
     if (std::is_same<Rng, RefRng>::value) {
         if (!a.pixel_rng) return cudaErrorInvalidValue;
         init_pixel_rng_kernel<<<(npix + 255) / 256, 256, 0, st>>>(W, H, (long long)a.seed, a.sample_offset, a.pixel_rng);
     }
-    cudaError_t e;
     // camera rays are generated inside the first bounce kernel when the RNG is counter-based
     // (large scenes, flag 32: the primary rays go through raygen + the persistent walk kernel as well — measured
     // 172.4 vs 169.3 ms per step on the 1 M-triangle scene, so the fused first bounce stays the default)
     const bool fuse_primary = fused && std::is_same<Rng, PcgRng>::value && !(walk_kernel && (a.flags & 32));
-    const int g_primary = persistent_grid((const void *)shade_kernel<R, PcgRng, 4>, T, smem_bvh);
-    const int g_primary_small = planar ? persistent_grid((const void *)shade_kernel<R, PcgRng, 6>, T, smem_bvh_small) : 0;
     // small scenes: primary rays use the scan/box records too unless B2RT_PATH_PRIMARY_WALK asks for the LBVH walk
     const bool primary_scan = planar && S.scan_incoherent && !(a.flags & 4);
-    const int g_primary_scan = planar ? persistent_grid((const void *)shade_kernel<R, PcgRng, 5>, T, smem_scan) : 0;
+    if ((e = persistent_grid((const void *)shade_kernel<R, PcgRng, 4>, T, smem_bvh, &g_primary))) return e;
+    if (planar) {
+        if ((e = persistent_grid((const void *)shade_kernel<R, PcgRng, 6>, T, smem_bvh_small, &g_primary_small))) return e;
+        if ((e = persistent_grid((const void *)shade_kernel<R, PcgRng, 5>, T, smem_scan, &g_primary_scan))) return e;
+    }
     if (sort_rays) iota_kernel<<<g_simple, T, 0, st>>>((int)((size_t)npix * wave), iota);
     for (int done = 0; done < a.spp_local; done += wave) {
         int k = a.spp_local - done < wave ? a.spp_local - done : wave;
@@ -211,7 +235,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             } else if (fused) {
                 prof_begin(kShade, st);
                 if (scan && planar) shade_kernel<R, Rng, 3><<<g_fuse_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth, PA);
-                else if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);
+                else if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, smem_generic, st>>>(S, Q, buf, b, a.max_depth, PA);
                 else shade_kernel<R, Rng, 1><<<g_fuse_bvh, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth, PA);
                 prof_end(st);
                 launches -= 1;

@@ -527,8 +527,11 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     float4 *cursor = s_top;
     if (WALK) { stage_top(S, s_top); cursor += 4 * S.n_top; }
     const float4 *s_scan = nullptr, *s_surf = nullptr;
-    // the scan records are what PLANAR modes intersect; walking modes keep them for the occluder hints
-    if (sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && (PLANAR || S.occl_hint)) {
+    // the scan records are what PLANAR modes intersect; MODE 6 and the generic scan (MODE 2) keep them for the
+    // occluder hints.  Only these launches pay for the bytes (rt_api.cuh): MODE 0 / 1 / 4 carry generic hints
+    // (codes >= 128) and never stage scan records
+    constexpr bool STAGE_SCAN = PLANAR || MODE == 6 || MODE == 2;
+    if (STAGE_SCAN && sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && (PLANAR || S.occl_hint)) {
         stage_scan(S, cursor); s_scan = cursor; cursor += 4 * (S.n_scan + S.n_box);
     }
     if (SURF) { stage_surf(S, cursor); s_surf = cursor; }

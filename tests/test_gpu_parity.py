@@ -93,9 +93,22 @@ def test_box_records_equal_planar_records(scene, cornell):
     a, ra = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=2, scan_boxes=True)
     b, rb = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=2, scan_boxes=False)
     same = a == b
-    # ~0.4 % of these rays start INSIDE a cube and reach the coplanar overlapping faces (cube 1 top / cube 2
-    # bottom, cube 1 bottom / floor): same distance, either label is a correct closest hit (checked below)
-    assert same.mean() > 0.995, f"{np.count_nonzero(~same)} of {n} ids differ"
+    # Documented tie case: ~0.4 % of these rays start INSIDE a cube and reach COINCIDENT faces
+    # (cube 1 top / cube 2 bottom at y = -9.4, cube 1 bottom / floor at y = -15).  The two surfaces are the same
+    # set of points; which label wins is decided by the last bit of two differently rounded distances in every
+    # formulation, the reference's float64 one included.  Every such flip must be between coplanar primitives at
+    # the same distance; on all other rays the two scans must agree to 0.9995.
+    plane = _prim_planes(pk)
+    flips = ~same & (a >= 0) & (b >= 0)
+    fa, fb = plane[a[flips]], plane[b[flips]]
+    parallel = np.abs(np.abs((fa[:, :3] * fb[:, :3]).sum(1)) - 1.0) < 1e-5
+    sgn = np.sign((fa[:, :3] * fb[:, :3]).sum(1))
+    coincident = parallel & (np.abs(fa[:, 3] - sgn * fb[:, 3]) < 1e-4)
+    tie = np.zeros(n, dtype=bool)
+    tie[np.flatnonzero(flips)[coincident]] = True
+    assert (np.abs(ra[tie, 0] - rb[tie, 0]) <= 1e-4 * np.maximum(1.0, rb[tie, 0])).all()
+    assert tie.sum() < 0.006 * n
+    assert same[~tie].mean() > 0.9995, f"{np.count_nonzero(~same & ~tie)} of {n} non-tie ids differ"
     both = same & (a >= 0)
     # float32 origins are known to ulp(15) ~ 1e-6, so a grazing hit's distance is only defined to ~1e-6 / |cos|
     # in either formulation; beyond that the two must agree to float32 rounding
@@ -111,6 +124,21 @@ def test_box_records_equal_planar_records(scene, cornell):
     assert np.count_nonzero((a >= 0) != (b >= 0)) <= 40          # silhouette edges of the open box, 0.02 %
     oa, _ = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=2, any_hit=True, scan_boxes=True)
     assert np.mean((oa >= 0) == (b >= 0)) > 0.9999
+
+
+def _prim_planes(pk):
+    """(unit normal, offset) per packed primitive; spheres get a zero row (never coplanar with anything)."""
+    out = np.zeros((pk.n_prims, 4))
+    R = pk.rect.reshape(-1, 4, 4)
+    for i in range(pk.n_rect):
+        nrm = R[i, 1, :3] / np.linalg.norm(R[i, 1, :3])
+        out[i] = (*nrm, nrm @ R[i, 0, :3])
+    T = pk.tri.reshape(-1, 3, 4)
+    base = pk.n_rect + pk.n_sphere
+    for i in range(pk.n_tri):
+        nrm = np.cross(T[i, 1, :3], T[i, 2, :3]); nrm /= np.linalg.norm(nrm)
+        out[base + i] = (*nrm, nrm @ T[i, 0, :3])
+    return out
 
 
 def _scan_and_quads(pk):
