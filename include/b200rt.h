@@ -50,6 +50,9 @@ extern "C" {
 #define B2RT_PATH_WALK_PRIMARY 32 /* large scenes: primary rays too go through raygen + the persistent walk kernel instead of
                                      the fused first-bounce kernel (measured slightly slower: coherent rays need no re-fetch) */
 
+#define B2RT_PATH_COUNT_TESTS 64  /* measurement passes: the persistent walk kernel tallies its box and leaf steps into
+                                     d_counters[8] / [9] (a separate kernel instantiation: the timed kernels carry no counters) */
+
 /* rng modes for b2rt_render_path */
 #define B2RT_RNG_PCG       0 /* counter-based: stream keyed by (pixel, global sample index, seed)        */
 #define B2RT_RNG_REFERENCE 1 /* the reference's int64 xorshift, per-pixel sequential (cuda_path_tracer.py:28,61-71) */
@@ -194,9 +197,12 @@ int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, 
  * d_pixel_rng (int64[H*W], caller-zeroed before sample 0... see DESIGN.md) carries the per-pixel state.
  * flags: B2RT_PATH_UNFUSED runs extend and shade as separate kernels through the hit stream (the default
  * fuses them: closest hit and shading in one kernel per bounce).
- * d_counters (optional) uint64[8], accumulated: [0] paths, [1] closest-hit rays, [2] shadow rays answered
+ * d_counters (optional) uint64[16], accumulated: [0] paths, [1] closest-hit rays, [2] shadow rays answered
  * (queued + resolved by the occluder cache), [3] unshadowed light samples, [4] kernel launches made by this
- * call, [5] shadow rays resolved by the occluder cache without being queued.
+ * call, [5] shadow rays resolved by the occluder cache without being queued, [6] camera rays answered by the
+ * scene-bounds slab test alone (no record scan), [7] shaded path segments (closest hits that were shaded),
+ * [8] / [9] per-lane box steps / leaf steps of the persistent walk kernel (only with B2RT_PATH_COUNT_TESTS),
+ * [10..15] reserved (zero).
  */
 int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
                      int32_t spp_local, int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth,

@@ -178,10 +178,14 @@ class B200PathTracer(_B200Base):
                  fused: bool = True, occluder_hints: bool = True, sort_rays: bool = True, progressive: bool = False,
                  scan_boxes: bool = True, primary_walk: bool = False, surface_records: bool = True,
                  fused_walk: bool = False, walk_primary: bool = False, rects_outside: bool = True,
-                 lbvh_rotations: bool = True):
+                 lbvh_rotations: bool = True, distributed: bool = True, count_tests: bool = False):
         super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints, scan_boxes,
                          surface_records, rects_outside, lbvh_rotations)
-        self.flags = (0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_walk else 0) | (8 if fused_walk else 0) | (32 if walk_primary else 0)
+        self.flags = ((0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_walk else 0) | (8 if fused_walk else 0)
+                      | (32 if walk_primary else 0) | (64 if count_tests else 0))
+        # distributed=False: render every sample on this GPU even inside a torch.distributed job (the N-GPU == 1-GPU
+        # image checks compare a split render with this)
+        self.distributed = bool(distributed)
         # progressive=True: successive render() calls with the same size ADD their samples (global sample
         # indices continue where the last call stopped) instead of discarding the previous frame — the
         # accumulation the reference's frame_count reseed hints at (cuda_path_tracer.py:28,739,809)
@@ -204,7 +208,7 @@ class B200PathTracer(_B200Base):
     def prepare(self, scene, camera, settings, want_sumsq: bool = False) -> dict:
         ds = self._upload(scene, camera)
         W, H, spp, depth = settings.width, settings.height, settings.samples_per_pixel, settings.max_depth
-        rank, world = dist.rank_world()
+        rank, world = self._rank_world()
         spp_local, offset = dist.split_samples(spp, rank, world)
         done = 0
         if self.progressive:
@@ -228,7 +232,7 @@ class B200PathTracer(_B200Base):
         st = dict(ds=ds, W=W, H=H, spp=spp, depth=depth, spp_local=spp_local, offset=offset, wave=wave,
                   accum=torch.zeros(W * H * 4, dtype=real, device=self.device),
                   accum_sq=torch.zeros(W * H * 4, dtype=real, device=self.device) if want_sumsq else None,
-                  counters=torch.zeros(8, dtype=torch.int64, device=self.device),
+                  counters=torch.zeros(16, dtype=torch.int64, device=self.device),
                   pixel_rng=(torch.zeros(W * H, dtype=torch.int64, device=self.device)
                              if self.rng_mode == _lib.RNG_REFERENCE else None),
                   u8=torch.empty(W * H * 3, dtype=torch.uint8, device=self.device),
@@ -236,6 +240,13 @@ class B200PathTracer(_B200Base):
         st["spp_done_before"] = done
         st["prog_key"] = (id(scene), tuple(float(x) for x in ds.cam), W, H, depth)
         return st
+
+    def _rank_world(self):
+        return dist.rank_world() if self.distributed else (0, 1)
+
+    def _reduce(self, buf) -> None:
+        if self.distributed:
+            dist.reduce_to_root(buf)
 
     def _fold_progressive(self, st: dict) -> None:
         """progressive mode: add this call's (already reduced) sums to the running total and resolve that."""
@@ -287,9 +298,9 @@ class B200PathTracer(_B200Base):
         with torch.cuda.device(self.device):
             st = self.prepare(scene, camera, settings, want_sumsq)
             self.accumulate(st)
-            dist.reduce_to_root(st["accum"])
+            self._reduce(st["accum"])
             if want_sumsq:
-                dist.reduce_to_root(st["accum_sq"])
+                self._reduce(st["accum_sq"])
             self._fold_progressive(st)
             torch.cuda.synchronize(self.device)
             self.frame_count += 1
@@ -306,9 +317,9 @@ class B200PathTracer(_B200Base):
             ev0.record()
             self.accumulate(st)
             ev1.record()
-            dist.reduce_to_root(st["accum"])
+            self._reduce(st["accum"])
             self._fold_progressive(st)
-            rank, world = dist.rank_world()
+            rank, world = self._rank_world()
             img = None
             if rank == 0:
                 img = self._image_from_u8(self.resolve(st), st["W"], st["H"])

@@ -110,7 +110,7 @@ template <typename R> struct PathLayout {
         L.stream_bytes = align256(n * sizeof(real4<R>));
         L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
         // per-bounce queue tails, unshadowed, culled + one ray-fetch counter per bounce (extend_walk_kernel)
-        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (2 * (size_t)max_depth + 4));
+        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (2 * (size_t)max_depth + 8));
         // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
         L.int_bytes = align256(n * sizeof(int));
         L.cub_bytes = 0;
@@ -146,7 +146,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.counts = counts;
     Q.unshadowed = counts + a.max_depth + 1;
     Q.culled = counts + a.max_depth + 2;
-    size_t counts_bytes = sizeof(unsigned long long) * (2 * (size_t)a.max_depth + 4);
+    size_t counts_bytes = sizeof(unsigned long long) * (2 * (size_t)a.max_depth + 8);
+    Q.tally = counts + 2 * a.max_depth + 4;                                 // [4] bounds-culled, hits, walk box / leaf steps
     unsigned long long *fetch = counts + a.max_depth + 3;                   // [max_depth] dynamic-fetch cursors
     const bool sort_rays = S.sort_inv > 0.f && !(a.flags & 2);
     unsigned *keys = (unsigned *)(base + L.sort_off), *keys_sorted = (unsigned *)(base + L.sort_off + L.int_bytes);
@@ -179,7 +180,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     if ((e = persistent_grid((const void *)shadow_kernel<R>, T, smem_shadow, &g_shadow))) return e;
     // large scenes: incoherent bounces run the persistent walk kernel + the wavefront shade stage
     const bool walk_kernel = fused && sizeof(R) == 4 && !S.scan_incoherent && !(a.flags & 8);
-    if ((e = persistent_grid((const void *)extend_walk_kernel<R>, T, smem, &g_walk))) return e;
+    const bool count_tests = (a.flags & 64) != 0;
+    if ((e = persistent_grid(count_tests ? (const void *)extend_walk_kernel<R, true> : (const void *)extend_walk_kernel<R, false>, T, smem, &g_walk))) return e;
     if ((e = persistent_grid((const void *)accumulate_kernel<R>, T, 0, &g_simple))) return e;
 
     if (std::is_same<Rng, RefRng>::value) {
@@ -226,8 +228,12 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 launches -= 1;
             } else if (walk_kernel) {
                 prof_begin(kExtend, st);
-                extend_walk_kernel<R><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
-                                                                (unsigned *)(fetch + b));
+                if (count_tests)
+                    extend_walk_kernel<R, true><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
+                                                                          (unsigned *)(fetch + b), Q.tally + 2);
+                else
+                    extend_walk_kernel<R, false><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
+                                                                           (unsigned *)(fetch + b), nullptr);
                 prof_end(st);
                 prof_begin(kShade, st);
                 shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);
@@ -276,7 +282,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         prof_end(st);
         ++launches;
         if (a.counters) {
-            path_counters_kernel<<<1, 1, 0, st>>>(Q.counts, Q.unshadowed, Q.culled, a.max_depth,
+            path_counters_kernel<<<1, 1, 0, st>>>(Q.counts, Q.unshadowed, Q.culled, Q.tally, a.max_depth,
                                                   (long long)npix * k, launches + 1, a.counters);
         }
         if ((e = cudaGetLastError())) return e;

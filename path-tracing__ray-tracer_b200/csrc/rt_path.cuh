@@ -73,6 +73,7 @@ template <typename R> struct PathQueues {
     unsigned long long *counts;            // [max_depth + 1]
     unsigned long long *unshadowed;        // [1]
     unsigned long long *culled;            // [1] shadow rays answered by the occluder hint (never queued)
+    unsigned long long *tally;             // [2] camera rays answered by the scene-bounds test, shaded segments (hits)
     unsigned *keys;                        // sort key of every ray appended to the next queue (or nullptr)
     const int *perm;                       // permutation the current queue is read through (or nullptr)
 };
@@ -109,6 +110,12 @@ template <typename R> __device__ __forceinline__ int ray_count(const PathQueues<
 }
 template <typename R> __device__ __forceinline__ int shadow_count(const PathQueues<R> &Q, int bounce) {
     return (int)(Q.counts[bounce + 1] >> 32);
+}
+
+// per-thread statistic flushed once per warp at kernel end
+__device__ __forceinline__ void warp_flush(unsigned long long *counter, unsigned v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
 }
 
 // ------------------------------------------------------------------------------------ raygen
@@ -200,11 +207,15 @@ __device__ __forceinline__ void prefetch_tri(const SceneDev &S, int prim) {
 #ifndef B2RT_WALK_MIN_BLOCKS
 #define B2RT_WALK_MIN_BLOCKS 4     // resident CTAs/SM (47 registers; 5 measured equal)
 #endif
-template <typename R>
+// COUNT (B2RT_PATH_COUNT_TESTS, measurement passes only): per-lane box steps (two slab tests each) and leaf steps
+// (one primitive test each) are tallied into tally[0] / tally[1] — the executed-work and bytes-per-ray figures of
+// bench.py's 1 M-triangle configuration come from these, never from an estimate.
+template <typename R, bool COUNT>
 __global__ void __launch_bounds__(256, sizeof(R) == 4 ? B2RT_WALK_MIN_BLOCKS : 1)
 extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__restrict__ rd,
                    real4<R> *__restrict__ hit, const unsigned long long *__restrict__ count,
-                   const int *__restrict__ perm, unsigned *__restrict__ next) {
+                   const int *__restrict__ perm, unsigned *__restrict__ next, unsigned long long *tally) {
+    unsigned n_node = 0, n_leaf = 0;
     extern __shared__ float4 s_top[];
     stage_top(S, s_top);
     constexpr int kDone = (int)0x80000000;                       // below every leaf reference (~prim)
@@ -254,6 +265,7 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
 #pragma unroll
             for (int rep = 0; rep < B2RT_WALK_NODE_STEPS; ++rep) {
             if (ref >= 0) {
+                if (COUNT) ++n_node;
                 float4 n0, n1, n2, n3;
                 if (ref < S.n_top) {
                     const float4 *p = s_top + 4 * ref;
@@ -287,11 +299,13 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
             }
             }
         } else if (want_leaf) {
+            if (COUNT) ++n_leaf;
             test_prim<R, false>(S, ~ref, r, t_min, best);
             ref = stack[--sp];
         }
     }
     if (pos >= 0) hit[pos] = Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b);
+    if (COUNT) { warp_flush(tally, n_node); warp_flush(tally + 1, n_leaf); }
 }
 
 // cuda_sample_hemisphere_cosine (:139-180)
@@ -343,12 +357,6 @@ __device__ __forceinline__ void warp_append2(unsigned long long *counter, bool w
     if (want_ray) ray_slot = (int)(base & 0xffffffffULL) + __popc(mr & lt);
     if (want_shadow) shadow_slot = (int)(base >> 32) + __popc(ms & lt);
 }
-// per-thread statistic flushed once per warp at kernel end
-__device__ __forceinline__ void warp_flush(unsigned long long *counter, unsigned v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
-}
-
 // ------------------------------------------------------------------------------------ shade
 template <typename R> struct Segment {       // what one loop iteration of cuda_trace_path produces
     bool alive, want_shadow, culled;
@@ -540,7 +548,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     int n = PRIMARY ? P.W * P.H * P.spp_wave : ray_count(Q, bounce);
     if (PRIMARY && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)n;   // for the ray statistics
     int n_round = (n + 31) & ~31;                // whole warps iterate together (ballots in warp_append2)
-    unsigned n_culled = 0;
+    unsigned n_culled = 0, n_tally = 0;          // n_tally: shaded hits (low 16 bits) | bounds-culled camera rays << 16
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool valid = i < n;
         Segment<R> g;
@@ -589,10 +597,11 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             } else {
                 if constexpr (sizeof(R) == 4) {
                     // camera rays: one slab test of the scene bounds answers the (coherent) misses
-                    if (PRIMARY && misses_scene(S, r)) { h.t = 1000000.0f; h.prim = -1; h.a = 0.f; h.b = 0.f; }
+                    if (PRIMARY && misses_scene(S, r)) { h.t = 1000000.0f; h.prim = -1; h.a = 0.f; h.b = 0.f; n_tally += 0x10000u; }
                     else scan_small<false>(S, s_scan, r, 0.001f, 1000000.0f, h);
                 }
             }
+            n_tally += h.prim >= 0 ? 1u : 0u;
             shade_segment<R, Rng, PRIMARY, (WALK || MODE == 0) && !(sizeof(R) == 4 && MODE == 6), SURF>(S, Q, (PLANAR && !S.occl_hint) ? nullptr : s_scan, s_surf,
                                                                 r, h, slot, bounce, max_depth, g);
         }
@@ -612,6 +621,8 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         }
     }
     warp_flush(Q.culled, n_culled);
+    warp_flush(Q.tally, n_tally >> 16);
+    warp_flush(Q.tally + 1, n_tally & 0xffffu);
 }
 
 // ------------------------------------------------------------------------------------ shadow
@@ -680,13 +691,14 @@ static __global__ void iota_kernel(int n, int *out) {
 }
 
 static __global__ void path_counters_kernel(const unsigned long long *counts, const unsigned long long *unshadowed,
-                                     const unsigned long long *culled, int max_depth, long long paths,
-                                     unsigned long long launches, unsigned long long *out) {
+                                     const unsigned long long *culled, const unsigned long long *tally, int max_depth,
+                                     long long paths, unsigned long long launches, unsigned long long *out) {
     unsigned long long rays = 0, shadows = 0;
     for (int b = 0; b < max_depth; ++b) { rays += counts[b] & 0xffffffffULL; shadows += counts[b + 1] >> 32; }
     // [2] counts every shadow ray that was answered: queued ones plus those the occluder cache resolved
     out[0] += (unsigned long long)paths; out[1] += rays; out[2] += shadows + *culled; out[3] += *unshadowed;
-    out[4] += launches; out[5] += *culled;
+    out[4] += launches; out[5] += *culled; out[6] += tally[0]; out[7] += tally[1];
+    out[8] += tally[2]; out[9] += tally[3];
 }
 
 // mean -> ACES (cuda_tonemap :74-81) -> min(255, max(0, int(c*255))) (:56-58) -> V flip (:807)

@@ -10,6 +10,7 @@ if not os.path.isfile(os.path.join(REF, "main.py")):
     print(json.dumps({"unavailable": "baseline/_ref holds no reference checkout"})); sys.exit(0)
 W, H, D = 1920, 1080, 8
 spps = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "16,64").split(",")]
+PATH_ONLY = "path-only" in sys.argv[2:]         # bench.py: only the reference path tracer, nothing of ours
 os.chdir(REF); sys.path.insert(0, REF)
 out = {"config": f"reference cuda_path_raytracer vs b200rt, {W}x{H}, depth {D}, reference scene objects + JPEG textures"}
 try:
@@ -31,7 +32,7 @@ except Exception as e:                                            # numba may no
     scene = None
 sys.path.insert(0, os.path.join(ROOT, "path-tracing__ray-tracer_b200"))
 try:
-    if scene is not None:
+    if scene is not None and not PATH_ONLY:
         import b200rt.renderer  # noqa: F401  registers into the REFERENCE's RendererFactory (plugin.py)
         ours = RendererFactory.create("b200_path_tracer")
         ours.render(scene, cam, RenderSettings(W, H, 8, D))
@@ -44,7 +45,7 @@ except Exception as e:
     out["b200rt_error"] = f"{type(e).__name__}: {e}"[:400]
 # ---- the reference's default renderer (cuda_texture_raytracer) at its golden setting: 2000x1500, 25 spp, depth 16
 try:
-    if scene is not None:
+    if scene is not None and not PATH_ONLY:
         import numpy as np
         import renderers.cuda_texture_renderer  # noqa: F401
         W2, H2, S2, D2 = 2000, 1500, 25, 16
