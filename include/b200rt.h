@@ -50,6 +50,8 @@ extern "C" {
 #define B2RT_PATH_WALK_PRIMARY 32 /* large scenes: primary rays too go through raygen + the persistent walk kernel instead of
                                      the fused first-bounce kernel (measured slightly slower: coherent rays need no re-fetch) */
 
+#define B2RT_PATH_NO_PRIMARY_MASKS 128 /* small scenes: camera rays test every scan record behind one scene-bounds slab test
+                                     instead of the per-32-pixel-tile candidate masks (measurement / validation switch) */
 #define B2RT_PATH_COUNT_TESTS 64  /* measurement passes: the persistent walk kernel tallies its box and leaf steps into
                                      d_counters[8] / [9] (a separate kernel instantiation: the timed kernels carry no counters) */
 
@@ -115,8 +117,9 @@ typedef struct b2rt_scene {
      * box and are scanned one by one, the rest are box faces kept for (u, v) / triangle-id recovery and as
      * occluder hints — followed by n_scan_boxes box records of 4 float4:
      *   (m0.xyz, d0) (m1.xyz, d1) (m2.xyz, d2)   l_k = m_k.P + d_k in [-1, 1] inside the box
-     *   (bits(f0|f1<<8|f2<<16|f3<<24), bits(f4|f5<<8), -, -)   f[2k + (l_k == +1)] = planar record of that face, 255 = none;
-     *   the two upper bytes of the second word must be 0
+     *   (bits(f0|f1<<8|f2<<16|f3<<24), bits(f4|f5<<8), bits(flags), -)   f[2k + (l_k == +1)] = planar record of that
+     *   face, 255 = none; the two upper bytes of the second word must be 0; flags bit 0 = CLOSED (all six faces exist:
+     *   the kernels then use a three-slab test without per-face bookkeeping and recover the face from the hit point)
      * With n_scan_boxes == 0 set n_scan_loose = n_scan_prims. */
     int32_t n_scan_loose;
     int32_t n_scan_boxes;
@@ -202,7 +205,8 @@ int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, 
  * call, [5] shadow rays resolved by the occluder cache without being queued, [6] camera rays answered by the
  * scene-bounds slab test alone (no record scan), [7] shaded path segments (closest hits that were shaded),
  * [8] / [9] per-lane box steps / leaf steps of the persistent walk kernel (only with B2RT_PATH_COUNT_TESTS),
- * [10..15] reserved (zero).
+ * [10] canonical flops (box record 42, planar record 33, sphere 28) of the camera rays' masked record tests,
+ * [11..15] reserved (zero).
  */
 int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
                      int32_t spp_local, int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth,

@@ -52,6 +52,8 @@ def _p(a, ty):
 
 # ------------------------------------------------------------------------------ numba family
 def _kind(obj) -> str:
+    if hasattr(obj, "vertices") and hasattr(obj, "faces"):
+        return "mesh"
     if hasattr(obj, "anchor"):
         return "plane"
     if hasattr(obj, "radius"):
@@ -88,6 +90,7 @@ def nb_pack(scene, camera, with_textures: bool = True) -> NbPacked:
     tex_id = {p: i for i, p in enumerate(tex_paths)}
     planes, spheres, tris = [], [], []
     o_pl, o_sp, o_tr = [], [], []
+    mesh_blocks, mesh_order, n_mesh_tris = [], [], 0       # meshes go behind the individual triangles
     for idx, o in enumerate(scene.objects):
         k, m = _kind(o), o.material
         if k == "plane":
@@ -99,6 +102,26 @@ def nb_pack(scene, camera, with_textures: bool = True) -> NbPacked:
             spheres += [o.center.x, o.center.y, o.center.z, o.radius, m.color.x, m.color.y, m.color.z,
                         m.diffuse, m.specular, m.reflective, getattr(m, "refractive", 0.0), getattr(m, "ior", 1.0)]
             o_sp.append(idx)
+        elif k == "mesh":
+            # bulk triangles (b200rt.packer.TriangleMesh): the same 26 floats per triangle as _prepare_scene_data
+            # (:861-885), geometric normal as Triangle.__init__ computes it (core/geometry.py:130), default uvs (:869-874)
+            V = np.asarray(o.vertices, dtype=np.float64); F = np.asarray(o.faces, dtype=np.int64)
+            v0, v1, v2 = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+            nn = np.cross(v1 - v0, v2 - v0)
+            ln = np.linalg.norm(nn, axis=1, keepdims=True)
+            nn = np.divide(nn, ln, out=np.zeros_like(nn), where=ln > 0)
+            blk = np.zeros((F.shape[0], 26))
+            blk[:, 0:3], blk[:, 3:6], blk[:, 6:9], blk[:, 9:12] = v0, v1, v2, nn
+            blk[:, 12:18] = (m.color.x, m.color.y, m.color.z, m.diffuse, m.specular, m.reflective)
+            blk[:, 18], blk[:, 19] = 0.0, -1.0
+            if getattr(o, "uvs", None) is not None:
+                U = np.asarray(o.uvs, dtype=np.float64)
+                blk[:, 20:22], blk[:, 22:24], blk[:, 24:26] = U[F[:, 0]], U[F[:, 1]], U[F[:, 2]]
+            else:
+                blk[:, 20:26] = (0.0, 0.0, 1.0, 0.0, 1.0, 1.0)
+            mesh_blocks.append((len(tris) // 26, blk.astype(np.float32)))
+            n_mesh_tris += F.shape[0]
+            mesh_order.append(np.full(F.shape[0], idx, dtype=np.int32))
         else:
             has = 1.0 if m.texture is not None else 0.0
             tid = -1.0
@@ -110,7 +133,7 @@ def nb_pack(scene, camera, with_textures: bool = True) -> NbPacked:
                      o.normal.x, o.normal.y, o.normal.z, m.color.x, m.color.y, m.color.z,
                      m.diffuse, m.specular, m.reflective, has, tid] + uvs
             o_tr.append(idx)
-    data = [len(planes) // 20] + planes + [len(spheres) // 12] + spheres + [len(tris) // 26] + tris
+    data = [len(planes) // 20] + planes + [len(spheres) // 12] + spheres + [len(tris) // 26 + n_mesh_tris] + tris
     cam = [camera.origin.x, camera.origin.y, camera.origin.z,
            camera.lower_left_corner.x, camera.lower_left_corner.y, camera.lower_left_corner.z,
            camera.horizontal.x, camera.horizontal.y, camera.horizontal.z,
@@ -131,9 +154,13 @@ def nb_pack(scene, camera, with_textures: bool = True) -> NbPacked:
         if with_textures:
             chunks.append(px)
     tex = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
-    return NbPacked(np.array(data, dtype=np.float32), np.array(cam, dtype=np.float32),
-                    np.array(lights, dtype=np.float32), tex, np.array(info, dtype=np.int32),
-                    np.array(o_pl + o_sp + o_tr, dtype=np.int32))
+    scene_arr = np.array(data, dtype=np.float32)
+    order = np.array(o_pl + o_sp + o_tr, dtype=np.int32)
+    if mesh_blocks:
+        scene_arr = np.concatenate([scene_arr] + [b.reshape(-1) for _, b in mesh_blocks])
+        order = np.concatenate([order] + mesh_order)
+    return NbPacked(scene_arr, np.array(cam, dtype=np.float32),
+                    np.array(lights, dtype=np.float32), tex, np.array(info, dtype=np.int32), order)
 
 
 def _nb_args(pk: NbPacked):

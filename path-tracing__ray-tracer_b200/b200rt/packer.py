@@ -508,6 +508,8 @@ def group_scan_boxes(rec: np.ndarray, quads: list, tol: float = 1e-5):
         w = np.array([code[0] | code[1] << 8 | code[2] << 16 | code[3] << 24, code[4] | code[5] << 8],
                      dtype=np.uint32)
         out[b, 3, 0:2] = w.view(np.float32)
+        # third info word, bit 0: CLOSED box (all six faces exist) -> the kernels take the tag-free three-slab test
+        out[b, 3, 2] = np.array([1 if all(c != 255 for c in code[:6]) else 0], dtype=np.uint32).view(np.float32)[0]
     return rec[order].reshape(-1, 4), len(loose), out.reshape(-1, 4)
 
 

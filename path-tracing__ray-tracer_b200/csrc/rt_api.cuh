@@ -103,21 +103,23 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 constexpr int kSortBeginBit = B2RT_SORT_BEGIN_BIT;
 
 template <typename R> struct PathLayout {
-    size_t stream_bytes, counts_off, sort_off, int_bytes, cub_bytes, total;
+    size_t stream_bytes, counts_off, sort_off, int_bytes, cub_bytes, mask_off, total;
     static PathLayout make(int W, int H, int spp_per_wave, int max_depth) {
         PathLayout L;
         size_t n = (size_t)W * H * spp_per_wave;
         L.stream_bytes = align256(n * sizeof(real4<R>));
         L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
         // per-bounce queue tails, unshadowed, culled + one ray-fetch counter per bounce (extend_walk_kernel)
-        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (2 * (size_t)max_depth + 8));
+        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (2 * (size_t)max_depth + 12));
         // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
         L.int_bytes = align256(n * sizeof(int));
         L.cub_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, L.cub_bytes, (const unsigned *)nullptr, (unsigned *)nullptr,
                                         (const int *)nullptr, (int *)nullptr, (int)n, 0, 30);
         L.cub_bytes = align256(L.cub_bytes);
-        L.total = L.sort_off + 4 * L.int_bytes + L.cub_bytes;
+        // camera-ray candidate masks: one word per 32-pixel tile (small scenes)
+        L.mask_off = L.sort_off + 4 * L.int_bytes + L.cub_bytes;
+        L.total = L.mask_off + 2 * align256(((size_t)W * H / 32 + 1) * sizeof(unsigned));   // masks + non-empty tile list
         return L;
     }
 };
@@ -146,8 +148,9 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.counts = counts;
     Q.unshadowed = counts + a.max_depth + 1;
     Q.culled = counts + a.max_depth + 2;
-    size_t counts_bytes = sizeof(unsigned long long) * (2 * (size_t)a.max_depth + 8);
-    Q.tally = counts + 2 * a.max_depth + 4;                                 // [4] bounds-culled, hits, walk box / leaf steps
+    // cleared per wave: queue tails, unshadowed, culled, fetch cursors, tally[0..4]; tally[5..7] live for the whole call
+    size_t counts_bytes_wave = sizeof(unsigned long long) * (2 * (size_t)a.max_depth + 4 + 5);
+    Q.tally = counts + 2 * a.max_depth + 4;                                 // [8] bounds-culled, hits, walk box / leaf steps, sky records
     unsigned long long *fetch = counts + a.max_depth + 3;                   // [max_depth] dynamic-fetch cursors
     const bool sort_rays = S.sort_inv > 0.f && !(a.flags & 2);
     unsigned *keys = (unsigned *)(base + L.sort_off), *keys_sorted = (unsigned *)(base + L.sort_off + L.int_bytes);
@@ -174,7 +177,9 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     if ((e = persistent_grid((const void *)extend_kernel<R>, T, smem, &g_extend))) return e;
     if ((e = persistent_grid((const void *)shade_kernel<R, Rng, 0>, T, 0, &g_shade))) return e;
     if ((e = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem_bvh, &g_fuse_bvh))) return e;
-    if (planar) e = persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_scan, &g_fuse_scan);
+    // MODE 3 double-buffers its ray records in shared memory (cp.async)
+    const size_t smem_mode3 = smem_scan + ((B2RT_OPT_ASYNC && sizeof(R) == 4) ? 2 * (size_t)kAsyncStageBytes : 0);
+    if (planar) e = persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_mode3, &g_fuse_scan);
     else e = persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, smem_generic, &g_fuse_scan);
     if (e) return e;
     if ((e = persistent_grid((const void *)shadow_kernel<R>, T, smem_shadow, &g_shadow))) return e;
@@ -199,6 +204,20 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         if ((e = persistent_grid((const void *)shade_kernel<R, PcgRng, 6>, T, smem_bvh_small, &g_primary_small))) return e;
         if ((e = persistent_grid((const void *)shade_kernel<R, PcgRng, 5>, T, smem_scan, &g_primary_scan))) return e;
     }
+    // small float32 scenes: per-tile candidate masks for the camera rays (once per call; the masked-test statistics
+    // land in tally[5..6], which the per-wave memset below leaves alone)
+    unsigned *masks = nullptr;
+    int *tile_list = nullptr;
+    if ((e = cudaMemsetAsync(Q.tally + 5, 0, 3 * sizeof(unsigned long long), st))) return e;
+    if constexpr (sizeof(R) == 4) {
+        if (B2RT_OPT_MASKS && fuse_primary && primary_scan && W % 32 == 0 && !(a.flags & 128) &&
+            S.n_box + S.n_loose + S.n_sphere <= 32) {
+            masks = (unsigned *)(base + L.mask_off);
+            tile_list = (int *)(base + L.mask_off + align256(((size_t)W * H / 32 + 1) * sizeof(unsigned)));
+            primary_mask_kernel<<<(npix / 32 + 127) / 128, 128, 0, st>>>(S, make_cam<float>(cam), W, H, masks, Q.tally + 5);
+            tile_compact_kernel<<<1, 1024, 0, st>>>(masks, npix / 32, tile_list, Q.tally + 7);
+        }
+    }
     if (sort_rays) iota_kernel<<<g_simple, T, 0, st>>>((int)((size_t)npix * wave), iota);
     for (int done = 0; done < a.spp_local; done += wave) {
         int k = a.spp_local - done < wave ? a.spp_local - done : wave;
@@ -209,7 +228,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         PA.by_npix = FastDiv::make((unsigned)npix); PA.by_w = FastDiv::make((unsigned)W);
         PA.tiles_x = (W % 8 == 0 && H % 4 == 0) ? W / 8 : 0;
         PA.by_tiles = FastDiv::make((unsigned)(PA.tiles_x > 0 ? PA.tiles_x : 1));
-        if ((e = cudaMemsetAsync(counts, 0, counts_bytes, st))) return e;
+        PA.masks = masks; PA.tiles = tile_list; PA.n_tiles = Q.tally + 7;
+        if ((e = cudaMemsetAsync(counts, 0, counts_bytes_wave, st))) return e;
         if (!fuse_primary) {
             prof_begin(kRaygen, st);
             raygen_kernel<R, Rng><<<g_simple, T, 0, st>>>(c, W, H, k, a.sample_offset + done, a.seed, a.pixel_rng, Q);
@@ -240,7 +260,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 prof_end(st);
             } else if (fused) {
                 prof_begin(kShade, st);
-                if (scan && planar) shade_kernel<R, Rng, 3><<<g_fuse_scan, T, smem_scan, st>>>(S, Q, buf, b, a.max_depth, PA);
+                if (scan && planar) shade_kernel<R, Rng, 3><<<g_fuse_scan, T, smem_mode3, st>>>(S, Q, buf, b, a.max_depth, PA);
                 else if (scan) shade_kernel<R, Rng, 2><<<g_fuse_scan, T, smem_generic, st>>>(S, Q, buf, b, a.max_depth, PA);
                 else shade_kernel<R, Rng, 1><<<g_fuse_bvh, T, smem_bvh, st>>>(S, Q, buf, b, a.max_depth, PA);
                 prof_end(st);
@@ -278,12 +298,12 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             }
         }
         prof_begin(kAccumulate, st);
-        accumulate_kernel<R><<<g_simple, T, 0, st>>>(npix, k, Q.L, (real4<R> *)a.accum, (real4<R> *)a.accum_sq);
+        accumulate_kernel<R><<<g_simple, T, 0, st>>>(npix, k, Q.L, (real4<R> *)a.accum, (real4<R> *)a.accum_sq, B2RT_OPT_TILE_LIST ? masks : nullptr);
         prof_end(st);
         ++launches;
         if (a.counters) {
             path_counters_kernel<<<1, 1, 0, st>>>(Q.counts, Q.unshadowed, Q.culled, Q.tally, a.max_depth,
-                                                  (long long)npix * k, launches + 1, a.counters);
+                                                  (long long)npix * k, k, launches + 1, a.counters);
         }
         if ((e = cudaGetLastError())) return e;
     }

@@ -54,6 +54,21 @@ __device__ __forceinline__ void add_stream(float4 *p, float x, float y, float z)
     *p = make_float4(l.x + x, l.y + y, l.z + z, l.w);
 #endif
 }
+// the escaping path's sky term inside the bounce kernel: B2RT_OPT_RED_SKY=1 uses three scalar fire-and-forget
+// reductions (no scoreboard wait on a DRAM-resident line) instead of load + add + store
+#ifndef B2RT_OPT_RED_SKY
+#define B2RT_OPT_RED_SKY 0
+#endif
+__device__ __forceinline__ void add_sky(float4 *p, float x, float y, float z) {
+#if B2RT_OPT_RED_SKY
+    float *q = reinterpret_cast<float *>(p);
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(x) : "memory");
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q + 1), "f"(y) : "memory");
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q + 2), "f"(z) : "memory");
+#else
+    add_stream(p, x, y, z);
+#endif
+}
 __device__ __forceinline__ void add_stream(double4 *p, double x, double y, double z) {
     double4 l = *p;
     *p = make_double4(l.x + x, l.y + y, l.z + z, l.w);
@@ -67,6 +82,8 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #endif
 }
+
+__device__ __forceinline__ void add_sky(double4 *p, double x, double y, double z) { add_stream(p, x, y, z); }
 
 template <typename R> struct V3 {
     R x, y, z;

@@ -73,7 +73,7 @@ template <typename R> struct PathQueues {
     unsigned long long *counts;            // [max_depth + 1]
     unsigned long long *unshadowed;        // [1]
     unsigned long long *culled;            // [1] shadow rays answered by the occluder hint (never queued)
-    unsigned long long *tally;             // [2] camera rays answered by the scene-bounds test, shaded segments (hits)
+    unsigned long long *tally;             // [8] bounds-culled camera rays, shaded hits, walk box / leaf steps, sky records
     unsigned *keys;                        // sort key of every ray appended to the next queue (or nullptr)
     const int *perm;                       // permutation the current queue is read through (or nullptr)
 };
@@ -379,7 +379,15 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
         Q.L[slot] = Real4<R>::make(sky, sky, sky, R(0));
     }
     if (h.prim < 0) {                                                       // :234-239 sky
-        if (!FIRST) add_stream(Q.L + slot, thr.x * R(0.1), thr.y * R(0.1), thr.z * R(0.1));
+#if B2RT_OPT_SKYQ
+        // An escaping path has no shadow ray of its own at this bounce, so its sky term rides in the lane's free
+        // shadow-queue slot as a PRE-RESOLVED record (light index -1): the shadow kernel of this bounce adds it to
+        // L[slot] — same position in the per-slot add order as before, bit-identical sums.  The load -> add -> store
+        // chain on a DRAM-resident line left the bounce kernel (12.9 % of its stall samples, profiles/r2a_*).
+        if (!FIRST) { want_shadow = true; g.light = -1; s_o = r.o; s_d = r.d; s_c = {thr.x * R(0.1), thr.y * R(0.1), thr.z * R(0.1)}; }
+#else
+        if (!FIRST) add_sky(Q.L + slot, thr.x * R(0.1), thr.y * R(0.1), thr.z * R(0.1));
+#endif
     } else {
         Surface<R> sf;
         if constexpr (SURF && sizeof(R) == 4) make_surface_small(s_surf, r, h, sf);
@@ -482,6 +490,24 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
 #ifndef B2RT_PRIMARY_TILES
 #define B2RT_PRIMARY_TILES 1
 #endif
+#ifndef B2RT_OPT_SKYQ
+#define B2RT_OPT_SKYQ 0            // 1: escaping paths hand their sky term to the shadow kernel through the shadow queue instead of a
+                                   // read-modify-write of L[slot] in the bounce kernel.  Measured (profiles/r2b): bounce kernels 19.9 ->
+                                   // 19.4 ms per 128 spp but the shadow kernels 2.0 -> 4.0 ms: the stall samples on that RMW were hidden
+#endif
+#ifndef B2RT_OPT_ASYNC
+#define B2RT_OPT_ASYNC 1           // 0: plain streaming loads of the ray records at the top of each iteration
+#endif
+// Asynchronous double-buffered ray-record fetch (MODE 3): every thread copies the three 16 B records of its NEXT
+// grid-stride item global -> shared with cp.async (LDGSTS, no register staging) while it scans and shades the current
+// one; it only ever reads back its own slots, so cp.async.wait_group is all the synchronisation there is.
+// profiles/r2a_*: 15 % of the bounce kernel's stall samples sat on the first use of the just-issued queue loads.
+constexpr int kAsyncStageBytes = 3 * 256 * 16;       // per stage: 3 streams x 256 threads x 16 B
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #ifndef B2RT_OPT_SURF
 #define B2RT_OPT_SURF 1            // 0: generic make_surface in the small-scene kernels (measured 23.8 vs 22.3 ms)
 #endif
@@ -506,6 +532,143 @@ struct FastDiv {
     }
 };
 
+// ------------------------------------------------------------------------------------ camera-ray candidate masks
+// Small scenes, bounce 0: the 32 camera rays of a warp belong to 32 neighbouring pixels of one row and all samples of
+// a pixel stay inside its footprint, so most of the scan records cannot be hit at all (a Cornell pixel sees one or two
+// of the seven).  Once per render call every 32-pixel tile gets a bit mask of the records whose bounds reach into the
+// tile's pyramid (tile widened by half a pixel; a record is dropped only when all its corners lie outside ONE of the
+// four side planes by a relative margin: conservative).  Tiles with an empty mask (51 % of the Cornell image) are never
+// visited by bounce 0 at all: it iterates over the compact list of non-empty tiles, and accumulate_kernel adds their
+// sky samples itself (the same float additions in the same order, without L[slot] ever being written or read).
+// stats[0] += canonical flops of the masked record tests of one sample of every pixel, stats[1] += pixels with an
+// empty mask (bench.py: executed FP32 work).
+#ifndef B2RT_OPT_MASKS
+#define B2RT_OPT_MASKS 1
+#endif
+#ifndef B2RT_OPT_TILE_LIST
+#define B2RT_OPT_TILE_LIST 1       // 0: bounce 0 still visits every pixel (row-major) and looks its tile's mask up
+#endif
+__device__ __forceinline__ bool inv3(const float a[3][3], float inv[3][3]) {
+    const float c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1], c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2],
+                c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+    const float det = a[0][0] * c00 + a[0][1] * c01 + a[0][2] * c02;
+    if (!(fabsf(det) > 1e-30f)) return false;
+    const float id = 1.0f / det;
+    inv[0][0] = c00 * id; inv[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id; inv[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+    inv[1][0] = c01 * id; inv[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id; inv[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+    inv[2][0] = c02 * id; inv[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id; inv[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
+    return true;
+}
+static __global__ void __launch_bounds__(128)
+primary_mask_kernel(SceneDev S, Cam<float> cam, int W, int H, unsigned *__restrict__ masks, unsigned long long *stats) {
+    const int n_tiles = (W / 32) * H;
+    unsigned flops = 0, empty = 0;
+    for (int tile = blockIdx.x * blockDim.x + threadIdx.x; tile < n_tiles; tile += gridDim.x * blockDim.x) {
+        const int pix0 = tile * 32, y = pix0 / W, x0 = pix0 - y * W;
+        const float u0 = (x0 - 0.5f) / W, u1 = (x0 + 32.5f) / W, v0 = (y - 0.5f) / H, v1 = (y + 1.5f) / H;
+        const float us[4] = {u0, u1, u1, u0}, vs[4] = {v0, v0, v1, v1};
+        float c[4][3], cc[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < 4; ++k) {
+            c[k][0] = cam.llc.x + us[k] * cam.hor.x + vs[k] * cam.ver.x - cam.origin.x;
+            c[k][1] = cam.llc.y + us[k] * cam.hor.y + vs[k] * cam.ver.y - cam.origin.y;
+            c[k][2] = cam.llc.z + us[k] * cam.hor.z + vs[k] * cam.ver.z - cam.origin.z;
+            cc[0] += c[k][0]; cc[1] += c[k][1]; cc[2] += c[k][2];
+        }
+        float n[4][3];                                   // unit inward normals of the four side planes (through the eye)
+        for (int k = 0; k < 4; ++k) {
+            const float *a = c[k], *b = c[(k + 1) & 3];
+            float nx = a[1] * b[2] - a[2] * b[1], ny = a[2] * b[0] - a[0] * b[2], nz = a[0] * b[1] - a[1] * b[0];
+            float sgn = (nx * cc[0] + ny * cc[1] + nz * cc[2]) < 0.f ? -1.f : 1.f;
+            float il = sgn * rsqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-30f));
+            n[k][0] = nx * il; n[k][1] = ny * il; n[k][2] = nz * il;
+        }
+        const float ex = cam.origin.x, ey = cam.origin.y, ez = cam.origin.z;
+        const float kEps = 1e-4f;
+        unsigned mask = 0, bit = 0;
+        // box record j: corners C +- h0 +- h1 +- h2 with (h0 h1 h2) = M^-1, C = -M^-1 d
+        const float4 *bx = S.scan + 4 * S.n_scan;
+        for (int j = 0; j < S.n_box; ++j, ++bit) {
+            const float4 q0 = __ldg(bx + 4 * j), q1 = __ldg(bx + 4 * j + 1), q2 = __ldg(bx + 4 * j + 2);
+            const float m[3][3] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}};
+            float h[3][3];
+            bool keep = true;
+            if (inv3(m, h)) {
+                const float cx = -(h[0][0] * q0.w + h[0][1] * q1.w + h[0][2] * q2.w) - ex,
+                            cy = -(h[1][0] * q0.w + h[1][1] * q1.w + h[1][2] * q2.w) - ey,
+                            cz = -(h[2][0] * q0.w + h[2][1] * q1.w + h[2][2] * q2.w) - ez;
+                for (int k = 0; k < 4 && keep; ++k) {
+                    float ext = 0.f, scale = fabsf(cx) + fabsf(cy) + fabsf(cz);
+                    for (int a = 0; a < 3; ++a) {        // column a of M^-1 is half axis a
+                        ext += fabsf(n[k][0] * h[0][a] + n[k][1] * h[1][a] + n[k][2] * h[2][a]);
+                        scale += fabsf(h[0][a]) + fabsf(h[1][a]) + fabsf(h[2][a]);
+                    }
+                    if (n[k][0] * cx + n[k][1] * cy + n[k][2] * cz + ext < -kEps * scale) keep = false;
+                }
+            }
+            if (keep) { mask |= 1u << bit; flops += 42u; }
+        }
+        // loose planar record k: P(u, v) = A^-1 (cN, u - d1, v - d2), corners (0 | umax) x (0 | vmax)
+        for (int k2 = 0; k2 < S.n_loose; ++k2, ++bit) {
+            const float4 q0 = __ldg(S.scan + 4 * k2), q1 = __ldg(S.scan + 4 * k2 + 1), q2 = __ldg(S.scan + 4 * k2 + 2),
+                         q3 = __ldg(S.scan + 4 * k2 + 3);
+            const float m[3][3] = {{q0.x, q0.y, q0.z}, {q1.x, q1.y, q1.z}, {q2.x, q2.y, q2.z}};
+            float h[3][3];
+            bool keep = true;
+            if (inv3(m, h)) {
+                const float px = h[0][0] * q0.w - h[0][1] * q1.w - h[0][2] * q2.w - ex,
+                            py = h[1][0] * q0.w - h[1][1] * q1.w - h[1][2] * q2.w - ey,
+                            pz = h[2][0] * q0.w - h[2][1] * q1.w - h[2][2] * q2.w - ez;
+                for (int k = 0; k < 4 && keep; ++k) {
+                    const float du = q3.x * (n[k][0] * h[0][1] + n[k][1] * h[1][1] + n[k][2] * h[2][1]);
+                    const float dv = q3.y * (n[k][0] * h[0][2] + n[k][1] * h[1][2] + n[k][2] * h[2][2]);
+                    const float scale = fabsf(px) + fabsf(py) + fabsf(pz) +
+                                        q3.x * (fabsf(h[0][1]) + fabsf(h[1][1]) + fabsf(h[2][1])) +
+                                        q3.y * (fabsf(h[0][2]) + fabsf(h[1][2]) + fabsf(h[2][2]));
+                    if (n[k][0] * px + n[k][1] * py + n[k][2] * pz + fmaxf(du, 0.f) + fmaxf(dv, 0.f) < -kEps * scale) keep = false;
+                }
+            }
+            if (keep) { mask |= 1u << bit; flops += 33u; }
+        }
+        const float4 *sph = reinterpret_cast<const float4 *>(S.sphere);
+        for (int i = 0; i < S.n_sphere; ++i, ++bit) {
+            const float4 s0 = __ldg(sph + 2 * i);
+            const float cx = s0.x - ex, cy = s0.y - ey, cz = s0.z - ez;
+            bool keep = true;
+            for (int k = 0; k < 4 && keep; ++k)
+                if (n[k][0] * cx + n[k][1] * cy + n[k][2] * cz + fabsf(s0.w) <
+                    -kEps * (fabsf(cx) + fabsf(cy) + fabsf(cz) + fabsf(s0.w))) keep = false;
+            if (keep) { mask |= 1u << bit; flops += 28u; }
+        }
+        masks[tile] = mask;
+        empty += mask == 0u ? 32u : 0u;
+    }
+    // per-pixel figures: every one of the tile's 32 pixels tests the tile's records
+    warp_flush(stats, flops * 32u);
+    warp_flush(stats + 1, empty);
+}
+
+// Ordered compaction of the non-empty tiles (one CTA; 64 800 tiles at 1080p): bounce 0 walks this list in image order, so
+// concurrently running warps stay on neighbouring pixels, texels and L[slot] lines exactly as in the untiled sweep.
+// (A list in atomic-arrival order ran bounce 1 1.7x slower: profiles/r2e-r2f.)  *count = list length.
+static __global__ void __launch_bounds__(1024)
+tile_compact_kernel(const unsigned *__restrict__ masks, int n_tiles, int *__restrict__ tiles, unsigned long long *count) {
+    __shared__ int s_sum[1024];
+    const int t = threadIdx.x, chunk = (n_tiles + 1023) / 1024, lo = min(t * chunk, n_tiles), hi = min(lo + chunk, n_tiles);
+    int c = 0;
+    for (int i = lo; i < hi; ++i) c += masks[i] != 0u;
+    s_sum[t] = c;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {                   // inclusive Hillis-Steele scan
+        const int v = t >= off ? s_sum[t - off] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    int pos = s_sum[t] - c;
+    for (int i = lo; i < hi; ++i) if (masks[i] != 0u) tiles[pos++] = i;
+    if (t == 1023) *count = (unsigned long long)s_sum[1023];
+}
+
 template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fused into the first bounce
     Cam<R> cam;
     int W, H, spp_wave;
@@ -513,6 +676,9 @@ template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fu
     int tiles_x;                                 // > 0: 8 x 4 pixel tiles per warp (W % 8 == 0 and H % 4 == 0)
     long long first_sample;
     unsigned long long seed;
+    const unsigned *masks;                       // MODE 5: per-32-pixel-tile candidate masks (or nullptr)
+    const int *tiles;                            //         compact list of the non-empty tiles ...
+    const unsigned long long *n_tiles;           //         ... and its length (device memory: no host sync)
 };
 
 // MODE 0: wavefront "shade" stage reading the hit stream written by extend_kernel.
@@ -542,23 +708,66 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     if (STAGE_SCAN && sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && (PLANAR || S.occl_hint)) {
         stage_scan(S, cursor); s_scan = cursor; cursor += 4 * (S.n_scan + S.n_box);
     }
-    if (SURF) { stage_surf(S, cursor); s_surf = cursor; }
+    if (SURF) { stage_surf(S, cursor); s_surf = cursor; cursor += 5 * S.n_prims; }
+    constexpr bool ASYNC = B2RT_OPT_ASYNC && MODE == 3 && sizeof(R) == 4;
+    float4 *s_ray = cursor;                                                  // [2 stages][3 streams][256 threads]
     const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
     real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
-    int n = PRIMARY ? P.W * P.H * P.spp_wave : ray_count(Q, bounce);
-    if (PRIMARY && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)n;   // for the ray statistics
+    // tile-list mode (MODE 5 with candidate masks): item i = ((sample * non-empty tiles + tile index) * 32 + lane)
+    const bool TILED = PLANAR && PRIMARY && B2RT_OPT_MASKS && B2RT_OPT_TILE_LIST && P.masks != nullptr;
+    const unsigned n_act = TILED ? (unsigned)(*P.n_tiles & 0xffffffffULL) : 1u;
+    int n = PRIMARY ? (TILED ? (int)n_act * 32 * P.spp_wave : P.W * P.H * P.spp_wave) : ray_count(Q, bounce);
+    // ray statistics: every camera ray counts as answered, whether its tile was visited or not
+    if (PRIMARY && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)(P.W * P.H * P.spp_wave);
     int n_round = (n + 31) & ~31;                // whole warps iterate together (ballots in warp_append2)
     unsigned n_culled = 0, n_tally = 0;          // n_tally: shaded hits (low 16 bits) | bounds-culled camera rays << 16
+    int stage = 0;
+    if constexpr (ASYNC) {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i0 < n) {
+            cp_async16(s_ray + threadIdx.x, ro + i0);
+            cp_async16(s_ray + 256 + threadIdx.x, rd + i0);
+            cp_async16(s_ray + 512 + threadIdx.x, th + i0);
+        }
+        cp_async_commit();
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool valid = i < n;
+        real4<R> qa, qb, qc;
+        if constexpr (ASYNC) {
+            cp_async_wait_all();
+            const float4 *cur = s_ray + stage * 768 + threadIdx.x;
+            if (valid) { qa = cur[0]; qb = cur[256]; qc = cur[512]; }
+            stage ^= 1;
+            const int nx = i + gridDim.x * blockDim.x;
+            if (nx < n) {
+                float4 *nxt = s_ray + stage * 768 + threadIdx.x;
+                cp_async16(nxt, ro + nx); cp_async16(nxt + 256, rd + nx); cp_async16(nxt + 512, th + nx);
+            }
+            cp_async_commit();
+        }
         Segment<R> g;
         g.alive = false; g.want_shadow = false; g.culled = false; g.rng = 0; g.light = 0;
         int slot = 0;
+        unsigned mask = 0xffffffffu;
         if (valid) {
             Ray<R> r;
             if (PRIMARY) {                       // cuda_path_trace_kernel's sample set-up (:35-41)
-                const int npix = P.W * P.H, s = (int)P.by_npix.div((unsigned)i);
-                int pix = i - s * npix, x, y;
+                const int npix = P.W * P.H;
+                int s, pix, x, y;
+                if (TILED) {
+                    // sample-major like the untiled order: concurrently running warps touch neighbouring L[slot] lines.
+                    // (Tile-major order — the warps of a CTA on the same tile, consecutive samples — put their L lines
+                    // a multiple of npix * 16 B apart and ran bounce 0 AND bounce 1 ~60 % slower: profiles/r2e.)
+                    const unsigned g32 = (unsigned)i >> 5;
+                    s = (int)(g32 / n_act);
+                    const int tile = __ldg(P.tiles + (g32 - (unsigned)s * n_act));
+                    pix = tile * 32 + (i & 31);
+                    mask = __ldg(P.masks + tile);
+                } else {
+                    s = (int)P.by_npix.div((unsigned)i); pix = i - s * npix;
+                    if (PLANAR && B2RT_OPT_MASKS && P.masks) mask = __ldg(P.masks + (pix >> 5));
+                }
 #if B2RT_PRIMARY_TILES
                 if (WALK && P.tiles_x > 0) {
                     // LBVH walk: a warp covers an 8 x 4 pixel tile instead of 32 pixels of one row, so neighbouring
@@ -578,8 +787,12 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                 slot = s * npix + pix; g.rng = state; g.thr = {R(1), R(1), R(1)};
             } else {
                 // fused walk modes read through the sort permutation; the wavefront stage (MODE 0) reads queue order
-                const int j = (MODE != 0 && Q.perm) ? __ldg(Q.perm + i) : i;
-                real4<R> a = ld_stream(ro + j), b = ld_stream(rd + j), c = ld_stream(th + j);
+                real4<R> a, b, c;
+                if constexpr (ASYNC) { a = qa; b = qb; c = qc; }
+                else {
+                    const int j = (MODE != 0 && Q.perm) ? __ldg(Q.perm + i) : i;
+                    a = ld_stream(ro + j); b = ld_stream(rd + j); c = ld_stream(th + j);
+                }
                 r.o = xyz<R>(a); r.d = xyz<R>(b);
                 slot = (int)unpack_u<R>(a.w);
                 g.rng = unpack_u<R>(b.w);
@@ -596,9 +809,14 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                 scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
             } else {
                 if constexpr (sizeof(R) == 4) {
-                    // camera rays: one slab test of the scene bounds answers the (coherent) misses
-                    if (PRIMARY && misses_scene(S, r)) { h.t = 1000000.0f; h.prim = -1; h.a = 0.f; h.b = 0.f; n_tally += 0x10000u; }
-                    else scan_small<false>(S, s_scan, r, 0.001f, 1000000.0f, h);
+                    if constexpr (PRIMARY) {
+                        // camera rays: only the records that reach into this warp's 32-pixel tile (warp-uniform mask);
+                        // without masks one slab test of the scene bounds answers the (coherent) misses.  ONE inlined
+                        // scan either way: the kernel has to stay inside the 32 KB instruction cache.
+                        if (!(B2RT_OPT_MASKS && P.masks) && misses_scene(S, r)) { mask = 0u; n_tally += 0x10000u; }
+                        if (mask == 0u) { h.t = 1000000.0f; h.prim = -1; h.a = 0.f; h.b = 0.f; }
+                        else scan_small<false, true>(S, s_scan, r, 0.001f, 1000000.0f, h, mask);
+                    } else scan_small<false>(S, s_scan, r, 0.001f, 1000000.0f, h);
                 }
             }
             n_tally += h.prim >= 0 ? 1u : 0u;
@@ -609,8 +827,11 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         int si, ni;
         warp_append2(Q.counts + bounce + 1, g.alive, g.want_shadow, ni, si);
         if (g.want_shadow) {
-            st_stream(Q.so + si, Real4<R>::make(g.s_o.x, g.s_o.y, g.s_o.z, pack_int<R>((int64_t)slot)));
-            st_stream(Q.sd + si, Real4<R>::make(g.s_d.x, g.s_d.y, g.s_d.z, pack_int<R>((int64_t)g.light)));
+            // bit 31 of the slot word marks a pre-resolved record (sky term of an escaping path: nothing to trace)
+            const unsigned slot_word = (unsigned)slot | (g.light < 0 ? 0x80000000u : 0u);
+            st_stream(Q.so + si, Real4<R>::make(g.s_o.x, g.s_o.y, g.s_o.z, pack_int<R>((int64_t)slot_word)));
+            if (g.light >= 0)
+                st_stream(Q.sd + si, Real4<R>::make(g.s_d.x, g.s_d.y, g.s_d.z, pack_int<R>((int64_t)g.light)));
             st_stream(Q.sc + si, Real4<R>::make(g.s_c.x, g.s_c.y, g.s_c.z, R(0)));
         }
         if (g.alive) {
@@ -635,30 +856,36 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
     else if (planar) stage_scan(S, s_top);
     int n = shadow_count(Q, bounce);
     int n_round = (n + 31) & ~31;
-    unsigned n_lit = 0;
+    unsigned n_lit = 0, n_sky = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        bool lit = false;
+        bool lit = false, sky = false;
         if (i < n) {
-            real4<R> a = ld_stream(Q.so + i), b = ld_stream(Q.sd + i);
-            Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
-            prefetch_l2(Q.L + (int)unpack_u<R>(a.w));
-            Hit<R> h;
-            bool occluded;                                                          // :275-277 t_max = 1e6
-            if (!S.scan_incoherent) occluded = traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);
-            else if constexpr (sizeof(R) == 4) {
-                occluded = planar ? scan_small<true>(S, s_top, r, 0.001f, 1000000.0f, h)
-                                  : scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h);
-            } else occluded = scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h);
-            lit = !occluded;
-            if (lit) {
-                int slot = (int)unpack_u<R>(a.w);
+            real4<R> a = ld_stream(Q.so + i);
+            const unsigned slot_word = (unsigned)unpack_u<R>(a.w);
+            sky = (slot_word >> 31) != 0u;                   // pre-resolved: the sky term of a path that escaped
+            if (!sky) {
+                real4<R> b = ld_stream(Q.sd + i);
+                Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
+                Hit<R> h;
+                bool occluded;                                                      // :275-277 t_max = 1e6
+                if (!S.scan_incoherent) occluded = traverse<R, false, true>(S, s_top, r, R(0.001), R(1000000.0), h);
+                else if constexpr (sizeof(R) == 4) {
+                    occluded = planar ? scan_small<true>(S, s_top, r, 0.001f, 1000000.0f, h)
+                                      : scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h);
+                } else occluded = scan_all<R, false, true>(S, r, R(0.001), R(1000000.0), h);
+                lit = !occluded;
+            }
+            if (lit || sky) {
+                const int slot = (int)(slot_word & 0x7fffffffu);
                 real4<R> c = ld_stream(Q.sc + i);
                 add_stream(Q.L + slot, c.x, c.y, c.z);
             }
         }
         n_lit += lit ? 1u : 0u;
+        n_sky += sky ? 1u : 0u;
     }
     warp_flush(Q.unshadowed, n_lit);
+    warp_flush(Q.tally + 4, n_sky);
 }
 
 // ------------------------------------------------------------------------------------ accumulate / resolve
@@ -666,12 +893,15 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
 template <typename R>
 __global__ void __launch_bounds__(256)
 accumulate_kernel(int npix, int spp_wave, const real4<R> *__restrict__ L, real4<R> *__restrict__ accum,
-                  real4<R> *__restrict__ accum_sq) {
+                  real4<R> *__restrict__ accum_sq, const unsigned *__restrict__ masks) {
     for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
         // wave-local partial sum first: the float32 running sum then sees one add per wave, not per sample
         R sx = R(0), sy = R(0), sz = R(0), qx = R(0), qy = R(0), qz = R(0);
+        // tiles no camera ray of which can hit anything were never traced (primary_mask_kernel): every sample is the
+        // sky value bounce 0 would have stored, added here in the same order
+        const bool sky_only = masks != nullptr && __ldg(masks + (pix >> 5)) == 0u;
         for (int s = 0; s < spp_wave; ++s) {
-            real4<R> l = L[(size_t)s * npix + pix];
+            real4<R> l = sky_only ? Real4<R>::make(R(0.1), R(0.1), R(0.1), R(0)) : L[(size_t)s * npix + pix];
             sx += l.x; sy += l.y; sz += l.z;
             qx += l.x * l.x; qy += l.y * l.y; qz += l.z * l.z;
         }
@@ -692,13 +922,16 @@ static __global__ void iota_kernel(int n, int *out) {
 
 static __global__ void path_counters_kernel(const unsigned long long *counts, const unsigned long long *unshadowed,
                                      const unsigned long long *culled, const unsigned long long *tally, int max_depth,
-                                     long long paths, unsigned long long launches, unsigned long long *out) {
+                                     long long paths, int spp_wave, unsigned long long launches, unsigned long long *out) {
     unsigned long long rays = 0, shadows = 0;
     for (int b = 0; b < max_depth; ++b) { rays += counts[b] & 0xffffffffULL; shadows += counts[b + 1] >> 32; }
     // [2] counts every shadow ray that was answered: queued ones plus those the occluder cache resolved
+    shadows -= tally[4];                                     // pre-resolved sky records are not shadow rays
     out[0] += (unsigned long long)paths; out[1] += rays; out[2] += shadows + *culled; out[3] += *unshadowed;
     out[4] += launches; out[5] += *culled; out[6] += tally[0]; out[7] += tally[1];
     out[8] += tally[2]; out[9] += tally[3];
+    // [10] canonical flops of this wave's masked camera-ray record tests, [6] also counts rays of empty-mask tiles
+    out[10] += tally[5] * (unsigned long long)spp_wave; out[6] += tally[6] * (unsigned long long)spp_wave;
 }
 
 // mean -> ACES (cuda_tonemap :74-81) -> min(255, max(0, int(c*255))) (:56-58) -> V flip (:807)

@@ -395,6 +395,7 @@ def test_lbvh_builder_degenerate_inputs(kind):
     dict(scan_boxes=False),
     dict(fused=False, surface_records=False),
     dict(top_nodes=0),
+    dict(primary_masks=False),                   # camera rays scan every record behind the scene-bounds test
 ])
 def test_cornell_f32_every_kernel_mode_agrees(cornell, kwargs):
     scene, b = cornell
@@ -408,6 +409,9 @@ def test_cornell_f32_every_kernel_mode_agrees(cornell, kwargs):
     m0, m1 = base[..., :3].mean() / n, acc[..., :3].mean() / n
     # an independent RNG (the reference's xorshift) only agrees statistically; everything else replays the same paths
     assert abs(m1 - m0) / m0 < (0.12 if kwargs.get("rng") == "reference" else 0.02), (m0, m1)
+    if "primary_masks" in kwargs:
+        # the per-tile candidate masks only skip records that no ray of the tile can hit: bit-identical image
+        assert np.array_equal(acc, base) and np.array_equal(cnt[:6], cnt0[:6])
     if kwargs.get("rng") != "reference":
         # same counter-based streams: paths differ only where float32 rounding flips a decision
         assert np.array_equal(acc[..., :3][sky], base[..., :3][sky])
@@ -434,3 +438,18 @@ def test_large_top_level_copy_needs_smem_opt_in():
     a0, c0 = renderer.B200PathTracer(precision="f32", seed=1, top_nodes=0).render_accum(scene, cam, RenderSettings(64, 48, 8, 4))
     a1, c1 = renderer.B200PathTracer(precision="f32", seed=1, top_nodes=1024).render_accum(scene, cam, RenderSettings(64, 48, 8, 4))
     assert np.array_equal(a0, a1) and np.array_equal(c0[:4], c1[:4])
+
+
+@pytest.mark.parametrize("size", [(1920, 1080), (96, 54), (64, 37)])
+def test_primary_candidate_masks_are_conservative(cornell, size):
+    """Camera-ray candidate masks (rt_path.cuh:primary_mask_kernel) at sizes with W % 32 == 0 (masks on) and not
+    (masks off): the sums equal the unmasked scan bit for bit, at the headline size too."""
+    scene, b = cornell
+    W, H = size
+    cam = b.create_camera(W / H)
+    spp = 2 if W > 1000 else 16
+    a, ca = renderer.B200PathTracer(precision="f32", seed=11).render_accum(scene, cam, RenderSettings(W, H, spp, 8))
+    c, cc = renderer.B200PathTracer(precision="f32", seed=11, primary_masks=False).render_accum(scene, cam, RenderSettings(W, H, spp, 8))
+    assert np.array_equal(a, c) and np.array_equal(ca[:6], cc[:6])
+    if W % 32 == 0:
+        assert ca[10] > 0 and ca[10] < cc[0] * (3 * 42 + 33 + 3 * 28)      # fewer record tests than the full scan
