@@ -218,6 +218,24 @@ int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width
 int b2rt_resolve(int32_t precision, const void *d_accum, int32_t width, int32_t height, double spp_total,
                  int32_t tonemap, uint8_t *d_u8, void *stream);
 
+/* ---- multi-GPU: samples split across ranks, float buffers combined over NVLink (the reference is
+ *      single-GPU, cuda.select_device(0), cuda_path_tracer.py:743) ------------------------------------------- */
+/*
+ * Fused reduce + resolve over PEER memory.  h_peer_accum[p] = device pointer to rank p's float32 accumulation buffer
+ * (float4[H*W], device row order), all of them mapped into this process (symmetric / IPC memory).  The caller's rank
+ * sums rows [row0, row1) of every peer IN RANK ORDER, divides by spp_total, tone-maps, quantises and writes the FLIPPED
+ * bytes into d_u8_root (uint8[3*H*W], normally the root's image buffer: a peer pointer) and, when d_sum_root is not
+ * NULL, the float sums into d_sum_root (float4[H*W]).  With every rank taking H / n_peers rows this is reduce-scatter,
+ * resolve and gather in one kernel.  The caller orders it after all ranks' b2rt_render_path (a cross-rank barrier on
+ * the stream) and before the root reads the image (another one).  float32 only.
+ */
+int b2rt_reduce_resolve(const void *const *h_peer_accum, int32_t n_peers, int32_t width, int32_t height, int32_t row0,
+                        int32_t row1, double spp_total, int32_t tonemap, uint8_t *d_u8_root, void *d_sum_root, void *stream);
+
+/* ---- texture upload helper (replaces the RGB flattening of _prepare_texture_data, cuda_path_tracer.py:901-932) */
+/* d_rgb: n_texels packed RGB8 triples (4-byte aligned) -> d_rgbx: n_texels RGBX8 words (16-byte aligned) */
+int b2rt_expand_rgb8(const uint8_t *d_rgb, int64_t n_texels, uint32_t *d_rgbx, void *stream);
+
 /* ---- measurement helpers (no reference counterpart: the reference times render() with time.time(),
  *      main.py:89-91) ----------------------------------------------------------------------------------- */
 /* When on, b2rt_render_path brackets every kernel launch with CUDA events on its stream. */

@@ -17,7 +17,7 @@ EXPORTS = [
     "b2rt_last_error", "b2rt_version", "b2rt_device_info", "b2rt_lbvh_temp_bytes", "b2rt_lbvh_build",
     "b2rt_primary_hits", "b2rt_trace_rays", "b2rt_render_whitted_cpu", "b2rt_render_whitted_texture",
     "b2rt_path_workspace_bytes", "b2rt_render_path", "b2rt_resolve",
-    "b2rt_profile_enable", "b2rt_profile_read", "b2rt_fp32_peak",
+    "b2rt_profile_enable", "b2rt_profile_read", "b2rt_fp32_peak", "b2rt_reduce_resolve", "b2rt_expand_rgb8",
 ]
 
 
@@ -72,6 +72,8 @@ def load():
     lib.b2rt_profile_enable.argtypes = [i32]
     lib.b2rt_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i64)]
     lib.b2rt_fp32_peak.argtypes = [i32, C.POINTER(dbl), vp]
+    lib.b2rt_reduce_resolve.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, dbl, i32, vp, vp, vp]
+    lib.b2rt_expand_rgb8.argtypes = [vp, i64, vp, vp]
     for name in EXPORTS:
         if name not in ("b2rt_last_error",):
             getattr(lib, name).restype = C.c_int

@@ -46,7 +46,7 @@ class _TextureCache:
     Two levels.  (1) A persistent PINNED host copy of the decoded ``Texture.pixels`` (RGB8, all textures back to
     back), rebuilt only when the pixel arrays change identity — the reference re-reads and re-flattens its textures
     on every ``render()`` (``cuda_path_tracer.py:901-932``: 4.7 s of Python list building).  (2) The device copy:
-    one H2D copy of that pinned block plus a handful of elementwise kernels that expand RGB to RGBX.
+    one H2D copy of that pinned block plus one library kernel that expands RGB8 to RGBX8.
     ``enabled=False`` drops level 2, i.e. the textures are re-uploaded from pinned memory on every call (what
     bench.py's end-to-end leg does)."""
 
@@ -100,10 +100,11 @@ class _TextureCache:
         # (2) one H2D copy + RGB8 -> RGBX8 on the device (plumbing, not the hot path)
         rgb8 = torch.empty(self._pinned.numel(), dtype=torch.uint8, device=device)
         rgb8.copy_(self._pinned, non_blocking=True)
-        texels = torch.empty(max(1, n), dtype=torch.int32, device=device)
-        if n:
-            rgb = rgb8[: 3 * n].view(-1, 3).to(torch.int32)
-            texels[:n] = rgb[:, 0] | (rgb[:, 1] << 8) | (rgb[:, 2] << 16) | (255 << 24)
+        texels = torch.empty(max(4, n), dtype=torch.int32, device=device)
+        if n:                                             # RGB8 -> RGBX8: one kernel of libb200rt.so (b2rt_expand_rgb8)
+            lib = _lib.load()
+            _lib.check(lib.b2rt_expand_rgb8(rgb8.data_ptr(), n, texels.data_ptr(), current_stream_ptr(device)),
+                       "b2rt_expand_rgb8")
         info_dev = rgb8[self._info_off:].view(torch.int32)
         host = (None, self._info, {p: i for i, p in enumerate(paths)})
         self._key, self._val, self._host = key, (texels, info_dev), host
@@ -198,6 +199,7 @@ class B200PathTracer(_B200Base):
         self.wave_paths = int(wave_paths)
         self.frame_count = 0                    # like CUDAPathTracer.frame_count (:739,:809)
         self._ws = None
+        self._symm, self._symm_key = None, None
 
     def get_capabilities(self) -> List[str]:
         return ["path_tracing", "global_illumination", "monte_carlo_integration", "color_bleeding", "shadows",
@@ -230,13 +232,22 @@ class B200PathTracer(_B200Base):
             self._ws = None
             self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
         real = _torch_real(self.precision)
-        st = dict(ds=ds, W=W, H=H, spp=spp, depth=depth, spp_local=spp_local, offset=offset, wave=wave,
-                  accum=torch.zeros(W * H * 4, dtype=real, device=self.device),
+        # multi-GPU float32: accumulate into peer-accessible memory so that the fused reduce + resolve kernel can read it
+        symm = None
+        if world > 1 and self.precision == _lib.P_F32 and not self.progressive and not want_sumsq:
+            key = (W, H, str(self.device))
+            if self._symm_key != key:
+                self._symm, self._symm_key = dist.SymmetricImage.create(W * H, self.device), key
+            symm = self._symm
+        if symm is not None:
+            symm.accum.zero_()
+        st = dict(ds=ds, W=W, H=H, spp=spp, depth=depth, spp_local=spp_local, offset=offset, wave=wave, symm=symm,
+                  accum=symm.accum if symm is not None else torch.zeros(W * H * 4, dtype=real, device=self.device),
                   accum_sq=torch.zeros(W * H * 4, dtype=real, device=self.device) if want_sumsq else None,
                   counters=torch.zeros(16, dtype=torch.int64, device=self.device),
                   pixel_rng=(torch.zeros(W * H, dtype=torch.int64, device=self.device)
                              if self.rng_mode == _lib.RNG_REFERENCE else None),
-                  u8=torch.empty(W * H * 3, dtype=torch.uint8, device=self.device),
+                  u8=symm.u8 if symm is not None else torch.empty(W * H * 3, dtype=torch.uint8, device=self.device),
                   cam=_lib.dbl_array(ds.cam))
         st["spp_done_before"] = done
         st["prog_key"] = (id(scene), tuple(float(x) for x in ds.cam), W, H, depth)
@@ -293,6 +304,26 @@ class B200PathTracer(_B200Base):
                                          current_stream_ptr(self.device)), "b2rt_resolve")
         return st["u8"]
 
+    def finish(self, st: dict, tonemap: bool = True):
+        """Combine the ranks' sums and resolve the 8-bit image on the root (asynchronous on the current stream).
+
+        Multi-GPU float32: every rank runs the fused reduce + resolve kernel on its share of the rows, reading all ranks'
+        buffers over NVLink and writing the root's image (``dist.SymmetricImage``); otherwise one NCCL reduce to rank 0
+        and the resolve kernel there.  Returns the device image on rank 0, ``None`` elsewhere."""
+        rank, world = self._rank_world()
+        symm = st.get("symm")
+        if symm is not None:
+            row0, row1 = symm.rows(st["H"])
+            symm.barrier()                          # every rank has finished accumulating
+            _lib.check(self.lib.b2rt_reduce_resolve(symm.peer_ptrs, world, st["W"], st["H"], row0, row1, float(st["spp"]),
+                                                    1 if tonemap else 0, symm.root_u8_ptr, None,
+                                                    current_stream_ptr(self.device)), "b2rt_reduce_resolve")
+            symm.barrier()                          # the root's image is complete; the peers' sums may be overwritten
+            return st["u8"] if rank == 0 else None
+        self._reduce(st["accum"])
+        self._fold_progressive(st)
+        return self.resolve(st, tonemap) if rank == 0 else None
+
     def render_accum(self, scene, camera, settings, want_sumsq: bool = False):
         """float sums [H, W, 4] (device row order) + counters, without tone mapping (tests/analysis).
         With ``want_sumsq`` a third array holds the per-pixel sums of squared per-sample radiance."""
@@ -318,12 +349,11 @@ class B200PathTracer(_B200Base):
             ev0.record()
             self.accumulate(st)
             ev1.record()
-            self._reduce(st["accum"])
-            self._fold_progressive(st)
+            u8 = self.finish(st)
             rank, world = self._rank_world()
             img = None
             if rank == 0:
-                img = self._image_from_u8(self.resolve(st), st["W"], st["H"])
+                img = self._image_from_u8(u8, st["W"], st["H"])
             torch.cuda.synchronize(self.device)
             cnt = st["counters"].cpu().numpy()
             kernel_s = ev0.elapsed_time(ev1) * 1e-3

@@ -208,6 +208,21 @@ int b2rt_resolve(int32_t precision, const void *d_accum, int32_t width, int32_t 
     return e ? fail("b2rt_resolve", e) : 0;
 }
 
+int b2rt_reduce_resolve(const void *const *h_peer_accum, int32_t n_peers, int32_t width, int32_t height, int32_t row0,
+                        int32_t row1, double spp_total, int32_t tonemap, uint8_t *d_u8_root, void *d_sum_root, void *stream) {
+    if (!h_peer_accum || !d_u8_root) return fail_msg("reduce_resolve: NULL buffer");
+    if (row0 < 0 || row1 > height || width < 1) return fail_msg("reduce_resolve: bad row range");
+    cudaError_t e = b2rt::reduce_resolve_f32(h_peer_accum, n_peers, width, height, row0, row1, spp_total, tonemap,
+                                             d_u8_root, d_sum_root, S(stream));
+    return e ? fail("b2rt_reduce_resolve", e) : 0;
+}
+
+int b2rt_expand_rgb8(const uint8_t *d_rgb, int64_t n_texels, uint32_t *d_rgbx, void *stream) {
+    if (((size_t)d_rgb & 3) || ((size_t)d_rgbx & 15)) return fail_msg("expand_rgb8: d_rgb must be 4-byte, d_rgbx 16-byte aligned");
+    cudaError_t e = b2rt::expand_rgb8(d_rgb, n_texels, d_rgbx, S(stream));
+    return e ? fail("b2rt_expand_rgb8", e) : 0;
+}
+
 int b2rt_profile_enable(int32_t on) {
     b2rt::ProfState *p = b2rt::prof_state();
     if (!p) return fail_msg("b2rt_profile_enable: no current device");

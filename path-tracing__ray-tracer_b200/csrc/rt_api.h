@@ -27,6 +27,11 @@ struct PathArgs {
     unsigned long long *counters;
 };
 
+// float32-only helpers (rt_f32.cu)
+cudaError_t reduce_resolve_f32(const void *const *peer_accum, int n_peers, int W, int H, int row0, int row1, double spp,
+                               int tonemap, uint8_t *root_u8, void *root_sum, cudaStream_t st);
+cudaError_t expand_rgb8(const uint8_t *rgb, long long n_texels, uint32_t *rgbx, cudaStream_t st);
+
 template <typename R> struct Api {
     static cudaError_t primary_hits(const b2rt_scene *s, const double *cam, int W, int H, double du, double dv,
                                     double t_min, double t_max, int use_bvh, int *ids, double *tt, cudaStream_t st);

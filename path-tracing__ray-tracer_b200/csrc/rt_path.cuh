@@ -953,4 +953,76 @@ resolve_kernel(const real4<R> *__restrict__ accum, int W, int H, R spp, int tone
     }
 }
 
+// ------------------------------------------------------------------------------------ multi-GPU: fused reduce + resolve
+// The float accumulation buffers of all ranks live in peer-accessible (symmetric) memory.  Rank g sums rows
+// [row0, row1) of EVERY rank's buffer over NVLink — in rank order, so the result does not depend on timing — applies
+// the resolve epilogue (mean, ACES, quantise, V flip) and stores the bytes straight into the root's image buffer:
+// the reduce-scatter, the resolve and the gather of SURVEY 8e in one kernel, no float image ever crosses the link
+// twice.  Four pixels per thread: 4 x 16 B loads per peer, 12 B of packed output.
+constexpr int kMaxPeers = 16;
+struct PeerAccum { const float4 *p[kMaxPeers]; };
+
+__device__ __forceinline__ unsigned quant_aces(float v, int tonemap) {
+    if (tonemap) v = (v * (2.51f * v + 0.03f)) / (v * (2.43f * v + 0.59f) + 0.14f);
+    long long q = (long long)(v * 255.0f);
+    return (unsigned)(q < 0 ? 0 : (q > 255 ? 255 : q));
+}
+
+static __global__ void __launch_bounds__(256)
+reduce_resolve_kernel(PeerAccum peers, int n_peers, int W, int H, int row0, int row1, float spp, int tonemap,
+                      uint8_t *__restrict__ root_u8, float4 *__restrict__ root_sum) {
+    const int groups_per_row = (W + 3) / 4, n = (row1 - row0) * groups_per_row;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        const int y = row0 + g / groups_per_row, x0 = (g - (g / groups_per_row) * groups_per_row) * 4;
+        const int cnt = min(4, W - x0);
+        float4 acc[4];
+        for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < n_peers; ++p) {
+            const float4 *src = peers.p[p] + (size_t)y * W + x0;
+            for (int k = 0; k < cnt; ++k) {
+                const float4 v = __ldcs(src + k);
+                acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z;
+            }
+        }
+        uint8_t b[12];
+        for (int k = 0; k < cnt; ++k) {
+            if (root_sum) root_sum[(size_t)y * W + x0 + k] = acc[k];
+            // the same operations as resolve_kernel<float>: a / spp first
+            b[3 * k] = (uint8_t)quant_aces(acc[k].x / spp, tonemap);
+            b[3 * k + 1] = (uint8_t)quant_aces(acc[k].y / spp, tonemap);
+            b[3 * k + 2] = (uint8_t)quant_aces(acc[k].z / spp, tonemap);
+        }
+        uint8_t *o = root_u8 + 3 * ((size_t)(H - 1 - y) * W + x0);
+        if (cnt == 4 && ((size_t)o & 3) == 0) {
+            unsigned w0 = b[0] | (b[1] << 8) | (b[2] << 16) | ((unsigned)b[3] << 24);
+            unsigned w1 = b[4] | (b[5] << 8) | (b[6] << 16) | ((unsigned)b[7] << 24);
+            unsigned w2 = b[8] | (b[9] << 8) | (b[10] << 16) | ((unsigned)b[11] << 24);
+            unsigned *ow = reinterpret_cast<unsigned *>(o);
+            ow[0] = w0; ow[1] = w1; ow[2] = w2;
+        } else {
+            for (int k = 0; k < 3 * cnt; ++k) o[k] = b[k];
+        }
+    }
+}
+
+// RGB8 -> RGBX8 (one 32-bit load per texel in the kernels), four texels per thread
+static __global__ void __launch_bounds__(256)
+expand_rgb8_kernel(const uint8_t *__restrict__ rgb, long long n_texels, uint32_t *__restrict__ rgbx) {
+    const long long n4 = n_texels / 4;
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(rgb);
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n4; g += (long long)gridDim.x * blockDim.x) {
+        const uint32_t a = __ldcs(in + 3 * g), b = __ldcs(in + 3 * g + 1), c = __ldcs(in + 3 * g + 2);
+        uint4 o;
+        o.x = (a & 0x00ffffffu) | 0xff000000u;
+        o.y = ((a >> 24) | (b << 8)) & 0x00ffffffu | 0xff000000u;
+        o.z = ((b >> 16) | (c << 16)) & 0x00ffffffu | 0xff000000u;
+        o.w = (c >> 8) | 0xff000000u;
+        reinterpret_cast<uint4 *>(rgbx)[g] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n_texels - 4 * n4)) {
+        const long long t = 4 * n4 + threadIdx.x;
+        rgbx[t] = rgb[3 * t] | (rgb[3 * t + 1] << 8) | (rgb[3 * t + 2] << 16) | 0xff000000u;
+    }
+}
+
 }  // namespace b2rt

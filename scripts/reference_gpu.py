@@ -24,8 +24,11 @@ try:
     t0 = time.perf_counter(); ref.render(scene, cam, RenderSettings(W, H, 1, D)); out["reference_first_call_incl_jit_s"] = time.perf_counter() - t0
     out["reference"] = {}
     for spp in spps:
-        t0 = time.perf_counter(); img = ref.render(scene, cam, RenderSettings(W, H, spp, D)); dt = time.perf_counter() - t0
-        out["reference"][str(spp)] = {"render_s": dt, "Mpaths_per_s": W * H * spp / dt / 1e6}
+        dts = []
+        for _ in range(2):                                        # the faster of two calls (host packing time varies)
+            t0 = time.perf_counter(); img = ref.render(scene, cam, RenderSettings(W, H, spp, D)); dts.append(time.perf_counter() - t0)
+        dt = min(dts)
+        out["reference"][str(spp)] = {"render_s": dt, "Mpaths_per_s": W * H * spp / dt / 1e6, "all_s": dts}
     img.save(os.path.join(ROOT, "gpurun_out", "reference_gpu.png")) if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
 except Exception as e:                                            # numba may not support this GPU / toolkit
     out["reference_error"] = f"{type(e).__name__}: {e}"[:400]
