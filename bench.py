@@ -127,18 +127,24 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
                 continue
+            try:
+                pw.append(float(r[3]))
+            except Exception:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "sm_mhz_min": sm[0] if sm else None, "power_w_median": pw[len(pw) // 2] if pw else None,
+                "power_w_max": pw[-1] if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def host_threads() -> int:
@@ -653,6 +659,9 @@ def main():
             "rays_per_path": {"traced": (closest + shadow - by_hint) / paths, "answered_by_hint": by_hint / paths,
                               "closest_hit": closest / paths, "shadow_queued": (shadow - by_hint) / paths},
             "clocks": clocks,
+            # what the bounce kernels themselves saw: cycle counter of CTA 0 against the global ns timer.  Some GPUs of the
+            # pool run sustained FP32 load slower at an unchanged nvidia-smi reading; this makes such a box visible
+            "sm_mhz_seen_by_kernels": (float(c0[11]) / float(c0[12]) * 1e3) if float(c0[12]) > 0 else None,
             "e2e": e2e,
             "gpu_launches": int(cnt[4]) // max(1, world) + args.steps,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": dom_gbs,

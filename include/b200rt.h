@@ -206,7 +206,8 @@ int b2rt_path_workspace_bytes(int32_t precision, int32_t width, int32_t height, 
  * scene-bounds slab test alone (no record scan), [7] shaded path segments (closest hits that were shaded),
  * [8] / [9] per-lane box steps / leaf steps of the persistent walk kernel (only with B2RT_PATH_COUNT_TESTS),
  * [10] canonical flops (box record 42, planar record 33, sphere 28) of the camera rays' masked record tests,
- * [11..15] reserved (zero).
+ * [11] / [12] SM cycles / nanoseconds that CTA 0 of every bounce kernel was resident (their ratio is the effective SM
+ * clock the kernels saw), [13..15] reserved (zero).
  */
 int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width, int32_t height,
                      int32_t spp_local, int64_t sample_offset, int32_t spp_per_wave, int32_t max_depth,

@@ -73,6 +73,7 @@ template <typename R> struct PathQueues {
     unsigned long long *counts;            // [max_depth + 1]
     unsigned long long *unshadowed;        // [1]
     unsigned long long *culled;            // [1] shadow rays answered by the occluder hint (never queued)
+    unsigned long long *clk;               // [2] sum of SM cycles / nanoseconds that CTA 0 of every bounce kernel ran (effective SM clock)
     unsigned long long *tally;             // [8] bounds-culled camera rays, shaded hits, walk box / leaf steps, sky records
     unsigned *keys;                        // sort key of every ray appended to the next queue (or nullptr)
     const int *perm;                       // permutation the current queue is read through (or nullptr)
@@ -696,6 +697,14 @@ __global__ void __launch_bounds__(256, sizeof(R) != 4 ? 1 : ((MODE == 3 || MODE 
 shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth, PrimaryArgs<R> P) {
     constexpr bool PRIMARY = MODE == 4 || MODE == 5 || MODE == 6, WALK = MODE == 1 || MODE == 4 || MODE == 6,
                    PLANAR = MODE == 3 || MODE == 5, SURF = B2RT_OPT_SURF && sizeof(R) == 4 && (PLANAR || MODE == 6);
+    // effective SM clock as the kernels see it: CTA 0's cycle counter against the global nanosecond timer (some GPUs of
+    // this pool run sustained FP32 load ~30 % slower at an unchanged nvidia-smi clock reading: bench.py reports both)
+    long long clk0 = 0;
+    unsigned long long ns0 = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        clk0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
     // shared memory: [BVH top levels (WALK)] [scan + box records] [surface records]
     extern __shared__ float4 s_top[];
     float4 *cursor = s_top;
@@ -844,6 +853,12 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     warp_flush(Q.culled, n_culled);
     warp_flush(Q.tally, n_tally >> 16);
     warp_flush(Q.tally + 1, n_tally & 0xffffu);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        atomicAdd(Q.clk, (unsigned long long)(clock64() - clk0));
+        atomicAdd(Q.clk + 1, ns1 - ns0);
+    }
 }
 
 // ------------------------------------------------------------------------------------ shadow
@@ -921,8 +936,8 @@ static __global__ void iota_kernel(int n, int *out) {
 }
 
 static __global__ void path_counters_kernel(const unsigned long long *counts, const unsigned long long *unshadowed,
-                                     const unsigned long long *culled, const unsigned long long *tally, int max_depth,
-                                     long long paths, int spp_wave, unsigned long long launches, unsigned long long *out) {
+                                     const unsigned long long *culled, const unsigned long long *tally,
+                                     const unsigned long long *clk, int max_depth, long long paths, int spp_wave, unsigned long long launches, unsigned long long *out) {
     unsigned long long rays = 0, shadows = 0;
     for (int b = 0; b < max_depth; ++b) { rays += counts[b] & 0xffffffffULL; shadows += counts[b + 1] >> 32; }
     // [2] counts every shadow ray that was answered: queued ones plus those the occluder cache resolved
@@ -932,6 +947,7 @@ static __global__ void path_counters_kernel(const unsigned long long *counts, co
     out[8] += tally[2]; out[9] += tally[3];
     // [10] canonical flops of this wave's masked camera-ray record tests, [6] also counts rays of empty-mask tiles
     out[10] += tally[5] * (unsigned long long)spp_wave; out[6] += tally[6] * (unsigned long long)spp_wave;
+    out[11] += clk[0]; out[12] += clk[1];
 }
 
 // mean -> ACES (cuda_tonemap :74-81) -> min(255, max(0, int(c*255))) (:56-58) -> V flip (:807)

@@ -30,5 +30,5 @@ ms = (C.c_double * 8)(); nl = (C.c_int64 * 8)(); lib.b2rt_profile_read(ms, nl); 
 cnt = st["counters"].cpu().numpy(); dt = e0.elapsed_time(e1) * 1e-3
 print({k: kw[k] for k in ("spp", "wave_paths", "scan", "top", "precision", "fused", "hints", "boxes", "pwalk", "surf")}, "wave", st["wave"],
       "Mpaths/s %.1f  Mrays/s %.1f  rays/path %.3f" % (cnt[0] / dt / 1e6, (cnt[1] + cnt[2]) / dt / 1e6, (cnt[1] + cnt[2]) / cnt[0]),
-      "clocks", clocks, "fp32 peak %.1f TF" % tfl.value,
+      "kernel-seen MHz %.0f" % (cnt[11] / max(1, cnt[12]) * 1e3), "clocks", clocks, "fp32 peak %.1f TF" % tfl.value,
       "ms/step: " + " ".join(f"{n}={ms[i] / kw['steps']:.1f}" for i, n in enumerate(["raygen", "extend", "shade", "shadow", "accum"])))

@@ -104,7 +104,7 @@ def test_headline_config_block_means_vs_oracle(cornell):
     v_gpu = np.maximum(sq[..., :3].astype(np.float64) / n - m_gpu ** 2, 0) * n / (n - 1)
     bm_ref, bm_gpu = blocks(m_ref), blocks(m_gpu)
     s2 = (blocks(v_ref) + blocks(v_gpu)) / n
-    lit = s2 > 1e-12
+    lit = blocks(v_ref) > 1e-9             # the oracle's float64 variance is exactly 0 on all-sky blocks (float32 sums carry rounding noise)
     z2 = (bm_gpu - bm_ref) ** 2 / np.where(lit, s2, 1)
     assert 0.75 < z2[lit].mean() < 1.3, z2[lit].mean()
     assert (np.abs(bm_gpu - bm_ref)[lit] <= 3 * np.sqrt(s2[lit])).mean() >= 0.99
