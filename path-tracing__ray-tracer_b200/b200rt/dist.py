@@ -58,7 +58,7 @@ class SymmetricImage:
         import os
         import torch.distributed as td
         rank, world = rank_world()
-        if world < 2:
+        if world < 2 or not (td.is_available() and td.is_initialized()):
             return None
         ok, obj = 1, None
         try:

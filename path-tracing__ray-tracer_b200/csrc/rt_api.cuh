@@ -102,15 +102,18 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 #endif
 constexpr int kSortBeginBit = B2RT_SORT_BEGIN_BIT;
 
+constexpr size_t kQueueSlack = (size_t)256 * 64 * kQueueChunk;      // any device with <= 256 SMs
+
 template <typename R> struct PathLayout {
     size_t stream_bytes, counts_off, sort_off, int_bytes, cub_bytes, mask_off, total;
     static PathLayout make(int W, int H, int spp_per_wave, int max_depth) {
         PathLayout L;
         size_t n = (size_t)W * H * spp_per_wave;
-        L.stream_bytes = align256(n * sizeof(real4<R>));
+        // + the dead remainders of every warp's last chunk (chunked append): <= 148 SMs x 64 resident warps x chunk
+        L.stream_bytes = align256((n + (size_t)kQueueSlack) * sizeof(real4<R>));
         L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
         // per-bounce queue tails, unshadowed, culled + one ray-fetch counter per bounce (extend_walk_kernel)
-        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (2 * (size_t)max_depth + 14));
+        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (3 * (size_t)max_depth + 16));
         // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
         L.int_bytes = align256(n * sizeof(int));
         L.cub_bytes = 0;
@@ -151,6 +154,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     // cleared per wave: queue tails, unshadowed, culled, fetch cursors, tally[0..4]; tally[5..7] live for the whole call
     size_t counts_bytes_wave = sizeof(unsigned long long) * (2 * (size_t)a.max_depth + 4 + 5);
     Q.clk = counts + 2 * a.max_depth + 12;                                  // [2] SM cycles / ns of CTA 0, cleared per wave
+    Q.dead = counts + 2 * a.max_depth + 14;                                 // [max_depth + 1] dead queue entries, cleared per wave
     Q.tally = counts + 2 * a.max_depth + 4;                                 // [8] bounds-culled, hits, walk box / leaf steps, sky records
     unsigned long long *fetch = counts + a.max_depth + 3;                   // [max_depth] dynamic-fetch cursors
     const bool sort_rays = S.sort_inv > 0.f && !(a.flags & 2);
@@ -231,7 +235,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         PA.by_tiles = FastDiv::make((unsigned)(PA.tiles_x > 0 ? PA.tiles_x : 1));
         PA.masks = masks; PA.tiles = tile_list; PA.n_tiles = Q.tally + 7;
         if ((e = cudaMemsetAsync(counts, 0, counts_bytes_wave, st))) return e;
-        if ((e = cudaMemsetAsync(Q.clk, 0, 2 * sizeof(unsigned long long), st))) return e;
+        if ((e = cudaMemsetAsync(Q.clk, 0, (2 + (size_t)a.max_depth + 1) * sizeof(unsigned long long), st))) return e;
         if (!fuse_primary) {
             prof_begin(kRaygen, st);
             raygen_kernel<R, Rng><<<g_simple, T, 0, st>>>(c, W, H, k, a.sample_offset + done, a.seed, a.pixel_rng, Q);
@@ -304,7 +308,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         prof_end(st);
         ++launches;
         if (a.counters) {
-            path_counters_kernel<<<1, 1, 0, st>>>(Q.counts, Q.unshadowed, Q.culled, Q.tally, Q.clk, a.max_depth,
+            path_counters_kernel<<<1, 1, 0, st>>>(Q.counts, Q.unshadowed, Q.culled, Q.tally, Q.clk, Q.dead, a.max_depth,
                                                   (long long)npix * k, k, launches + 1, a.counters);
         }
         if ((e = cudaGetLastError())) return e;

@@ -73,6 +73,7 @@ template <typename R> struct PathQueues {
     unsigned long long *counts;            // [max_depth + 1]
     unsigned long long *unshadowed;        // [1]
     unsigned long long *culled;            // [1] shadow rays answered by the occluder hint (never queued)
+    unsigned long long *dead;              // [max_depth + 1] unused (dead) entries inside the queues of bounce k: rays | shadow records << 32
     unsigned long long *clk;               // [2] sum of SM cycles / nanoseconds that CTA 0 of every bounce kernel ran (effective SM clock)
     unsigned long long *tally;             // [8] bounds-culled camera rays, shaded hits, walk box / leaf steps, sky records
     unsigned *keys;                        // sort key of every ray appended to the next queue (or nullptr)
@@ -111,6 +112,58 @@ template <typename R> __device__ __forceinline__ int ray_count(const PathQueues<
 }
 template <typename R> __device__ __forceinline__ int shadow_count(const PathQueues<R> &Q, int bounce) {
     return (int)(Q.counts[bounce + 1] >> 32);
+}
+
+// ---- chunked queue append (small-scene bounce kernels) ---------------------------------------------------------
+// ONE atomic per warp iteration on the queue tail was THE limit of the Cornell bounce kernels: every warp of the grid
+// hits the same 8 bytes ~0.8 G times a second, which is all one L2 atomic unit does (measured, profiles/r2m: a second
+// no-op atomicAdd on that word doubled the kernel time, 46.6 -> 95.1 ms; the rate differs by ~30 % between GPUs of the
+// pool, and so did the whole benchmark).  Here every warp owns a CHUNK of kQueueChunk slots in each queue and goes back
+// to the tail only when the chunk is used up (one atomic per ~5 iterations); an append that does not fit fills the old
+// chunk and continues in the new one, so the only unused slots are each warp's last chunk remainder, which the warp
+// marks dead (slot word -1) before it exits — consumers skip those, the statistics subtract them (Q.dead).
+constexpr int kQueueChunk = 128;
+struct WarpCursor { int ray_cur, ray_end, sh_cur, sh_end; };     // shared memory, one per warp, written by lane 0
+
+// refill path, out of line (the bounce kernels live next to the instruction-cache limit): takes a new chunk from the tail
+// word (32-bit half of the packed counter) and returns its base
+static __device__ __noinline__ int chunk_refill(unsigned *tail_word) {
+    unsigned nb = 0;
+    if ((threadIdx.x & 31u) == 0) nb = atomicAdd(tail_word, (unsigned)kQueueChunk);
+    return (int)__shfl_sync(0xffffffffu, nb, 0);
+}
+__device__ __forceinline__ int chunk_take(unsigned *tail_word, int &cur, int &end, unsigned m, unsigned lane) {
+    const int k = __popc(m), free_ = end - cur, rank = __popc(m & ((1u << lane) - 1u));
+    int slot = cur + rank;
+    cur += k;
+    if (k > free_) {                                             // warp-uniform
+        const int nb = chunk_refill(tail_word);
+        if (rank >= free_) slot = nb + (rank - free_);
+        cur = nb + (k - free_);
+        end = nb + kQueueChunk;
+    }
+    return slot;
+}
+__device__ __forceinline__ void warp_append_chunked(unsigned long long *tail, WarpCursor *wc, bool want_ray, bool want_shadow,
+                                                    int &ray_slot, int &shadow_slot) {
+    const unsigned mr = __ballot_sync(0xffffffffu, want_ray), ms = __ballot_sync(0xffffffffu, want_shadow);
+    ray_slot = shadow_slot = -1;
+    if ((mr | ms) == 0) return;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned *words = reinterpret_cast<unsigned *>(tail);        // little endian: [0] ray tail, [1] shadow tail
+    if (mr) {
+        int cur = wc->ray_cur, end = wc->ray_end;
+        const int slot = chunk_take(words, cur, end, mr, lane);
+        if (want_ray) ray_slot = slot;
+        if (lane == 0) { wc->ray_cur = cur; wc->ray_end = end; }
+    }
+    if (ms) {
+        int cur = wc->sh_cur, end = wc->sh_end;
+        const int slot = chunk_take(words + 1, cur, end, ms, lane);
+        if (want_shadow) shadow_slot = slot;
+        if (lane == 0) { wc->sh_cur = cur; wc->sh_end = end; }
+    }
+    __syncwarp();
 }
 
 // per-thread statistic flushed once per warp at kernel end
@@ -236,11 +289,13 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
         if (!exhausted && (__popc(idle) >= B2RT_WALK_REFILL)) {
             if (ref == kDone && pos >= 0)
                 hit[pos] = Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b);
+            // (taking the indices in per-warp chunks of 32 / 128 / 512 instead was measured at 63.3 / 64.4 / 69.7 ms per
+            // step against 62.5: this kernel is latency-bound, not bound by the cursor's atomic unit)
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(next, (unsigned)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned i = base + (unsigned)__popc(idle & lt);
             if (ref == kDone) {
-                const unsigned i = base + (unsigned)__popc(idle & lt);
                 pos = -1;
                 if (i < (unsigned)n) {
                     const int j = perm ? __ldg(perm + i) : (int)i;
@@ -354,6 +409,9 @@ __device__ __forceinline__ void warp_append2(unsigned long long *counter, bool w
     const unsigned lt = (1u << lane) - 1u;
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(mr) | ((unsigned long long)__popc(ms) << 32));
+#ifdef B2RT_TEST_ATOMIC2            // experiment: a second, no-op atomic on the SAME word (is the queue tail's L2 atomic unit the limit?)
+    if (lane == 0) atomicAdd(counter, 0ULL);
+#endif
     base = __shfl_sync(0xffffffffu, base, 0);
     if (want_ray) ray_slot = (int)(base & 0xffffffffULL) + __popc(mr & lt);
     if (want_shadow) shadow_slot = (int)(base >> 32) + __popc(ms & lt);
@@ -495,6 +553,9 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
 #define B2RT_OPT_SKYQ 0            // 1: escaping paths hand their sky term to the shadow kernel through the shadow queue instead of a
                                    // read-modify-write of L[slot] in the bounce kernel.  Measured (profiles/r2b): bounce kernels 19.9 ->
                                    // 19.4 ms per 128 spp but the shadow kernels 2.0 -> 4.0 ms: the stall samples on that RMW were hidden
+#endif
+#ifndef B2RT_OPT_CHUNKED
+#define B2RT_OPT_CHUNKED 1         // 0: one queue-tail atomic per warp iteration (warp_append2) in the small-scene kernels too
 #endif
 #ifndef B2RT_OPT_ASYNC
 #define B2RT_OPT_ASYNC 1           // 0: plain streaming loads of the ray records at the top of each iteration
@@ -730,6 +791,12 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     if (PRIMARY && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)(P.W * P.H * P.spp_wave);
     int n_round = (n + 31) & ~31;                // whole warps iterate together (ballots in warp_append2)
     unsigned n_culled = 0, n_tally = 0;          // n_tally: shaded hits (low 16 bits) | bounds-culled camera rays << 16
+    // small-scene kernels append through per-warp chunks (one tail atomic per ~5 iterations instead of one per iteration)
+    constexpr bool CHUNKED = B2RT_OPT_CHUNKED && PLANAR;
+    __shared__ WarpCursor s_wc[8];
+    WarpCursor *wc = s_wc + (threadIdx.x >> 5);
+    if (CHUNKED && (threadIdx.x & 31) == 0) { wc->ray_cur = wc->ray_end = wc->sh_cur = wc->sh_end = 0; }
+    if (CHUNKED) __syncwarp();
     int stage = 0;
     if constexpr (ASYNC) {
         const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -759,6 +826,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         g.alive = false; g.want_shadow = false; g.culled = false; g.rng = 0; g.light = 0;
         int slot = 0;
         unsigned mask = 0xffffffffu;
+        bool dead = false;
         if (valid) {
             Ray<R> r;
             if (PRIMARY) {                       // cuda_path_trace_kernel's sample set-up (:35-41)
@@ -807,7 +875,9 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                 g.rng = unpack_u<R>(b.w);
                 g.thr = xyz<R>(c);
                 prefetch_l2(Q.L + slot);         // a miss adds the sky term to L[slot]: DRAM round trip started now
+                dead = slot < 0;                 // unused remainder of a producer warp's last chunk
             }
+            if (!dead) {
             Hit<R> h;
             if (MODE == 0) {
                 real4<R> hrec = ld_stream(Q.hit + i);
@@ -831,10 +901,12 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             n_tally += h.prim >= 0 ? 1u : 0u;
             shade_segment<R, Rng, PRIMARY, (WALK || MODE == 0) && !(sizeof(R) == 4 && MODE == 6), SURF>(S, Q, (PLANAR && !S.occl_hint) ? nullptr : s_scan, s_surf,
                                                                 r, h, slot, bounce, max_depth, g);
+            }
         }
         n_culled += g.culled ? 1u : 0u;
         int si, ni;
-        warp_append2(Q.counts + bounce + 1, g.alive, g.want_shadow, ni, si);
+        if constexpr (CHUNKED) warp_append_chunked(Q.counts + bounce + 1, wc, g.alive, g.want_shadow, ni, si);
+        else warp_append2(Q.counts + bounce + 1, g.alive, g.want_shadow, ni, si);
         if (g.want_shadow) {
             // bit 31 of the slot word marks a pre-resolved record (sky term of an escaping path: nothing to trace)
             const unsigned slot_word = (unsigned)slot | (g.light < 0 ? 0x80000000u : 0u);
@@ -849,6 +921,17 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             st_stream(nt + ni, Real4<R>::make(g.thr.x, g.thr.y, g.thr.z, pack_int<R>((int64_t)(bounce + 1))));
             if ((WALK || MODE == 0) && Q.keys) Q.keys[ni] = ray_sort_key<R>(g.new_o, g.new_d, S.sort_inv);
         }
+    }
+    if constexpr (CHUNKED) {
+        // the unused remainder of this warp's last chunks: marked dead for the consumers, counted for the statistics
+        const int lane = threadIdx.x & 31;
+        const int rc = wc->ray_cur, re = wc->ray_end, sc = wc->sh_cur, se = wc->sh_end;
+#pragma unroll 1
+        for (int k = rc + lane; k < re; k += 32) st_stream(no + k, Real4<R>::make(R(0), R(0), R(0), pack_int<R>(-1)));
+#pragma unroll 1
+        for (int k = sc + lane; k < se; k += 32) st_stream(Q.so + k, Real4<R>::make(R(0), R(0), R(0), pack_int<R>(-1)));
+        if (lane == 0 && (re - rc) + (se - sc) > 0)
+            atomicAdd(Q.dead + bounce + 1, (unsigned long long)(re - rc) | ((unsigned long long)(se - sc) << 32));
     }
     warp_flush(Q.culled, n_culled);
     warp_flush(Q.tally, n_tally >> 16);
@@ -877,8 +960,9 @@ shadow_kernel(SceneDev S, PathQueues<R> Q, int bounce) {
         if (i < n) {
             real4<R> a = ld_stream(Q.so + i);
             const unsigned slot_word = (unsigned)unpack_u<R>(a.w);
-            sky = (slot_word >> 31) != 0u;                   // pre-resolved: the sky term of a path that escaped
-            if (!sky) {
+            const bool dead = slot_word == 0xffffffffu;      // unused remainder of a producer warp's last chunk
+            sky = !dead && (slot_word >> 31) != 0u;          // pre-resolved: the sky term of a path that escaped
+            if (!sky && !dead) {
                 real4<R> b = ld_stream(Q.sd + i);
                 Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
                 Hit<R> h;
@@ -937,9 +1021,13 @@ static __global__ void iota_kernel(int n, int *out) {
 
 static __global__ void path_counters_kernel(const unsigned long long *counts, const unsigned long long *unshadowed,
                                      const unsigned long long *culled, const unsigned long long *tally,
-                                     const unsigned long long *clk, int max_depth, long long paths, int spp_wave, unsigned long long launches, unsigned long long *out) {
+                                     const unsigned long long *clk, const unsigned long long *dead, int max_depth,
+                                     long long paths, int spp_wave, unsigned long long launches, unsigned long long *out) {
     unsigned long long rays = 0, shadows = 0;
-    for (int b = 0; b < max_depth; ++b) { rays += counts[b] & 0xffffffffULL; shadows += counts[b + 1] >> 32; }
+    for (int b = 0; b < max_depth; ++b) {
+        rays += (counts[b] & 0xffffffffULL) - (dead[b] & 0xffffffffULL);      // queue tails minus dead chunk remainders
+        shadows += (counts[b + 1] >> 32) - (dead[b + 1] >> 32);
+    }
     // [2] counts every shadow ray that was answered: queued ones plus those the occluder cache resolved
     shadows -= tally[4];                                     // pre-resolved sky records are not shadow rays
     out[0] += (unsigned long long)paths; out[1] += rays; out[2] += shadows + *culled; out[3] += *unshadowed;
