@@ -113,7 +113,7 @@ template <typename R> struct PathLayout {
         L.stream_bytes = align256((n + (size_t)kQueueSlack) * sizeof(real4<R>));
         L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
         // per-bounce queue tails, unshadowed, culled + one ray-fetch counter per bounce (extend_walk_kernel)
-        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (3 * (size_t)max_depth + 16));
+        L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (3 * (size_t)max_depth + 18));
         // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
         L.int_bytes = align256(n * sizeof(int));
         L.cub_bytes = 0;
@@ -155,6 +155,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     size_t counts_bytes_wave = sizeof(unsigned long long) * (2 * (size_t)a.max_depth + 4 + 5);
     Q.clk = counts + 2 * a.max_depth + 12;                                  // [2] SM cycles / ns of CTA 0, cleared per wave
     Q.dead = counts + 2 * a.max_depth + 14;                                 // [max_depth + 1] dead queue entries, cleared per wave
+    unsigned long long *tile_info = counts + 3 * a.max_depth + 15;          // [2] non-empty tiles, division constants (per call)
     Q.tally = counts + 2 * a.max_depth + 4;                                 // [8] bounds-culled, hits, walk box / leaf steps, sky records
     unsigned long long *fetch = counts + a.max_depth + 3;                   // [max_depth] dynamic-fetch cursors
     const bool sort_rays = S.sort_inv > 0.f && !(a.flags & 2);
@@ -214,13 +215,14 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     unsigned *masks = nullptr;
     int *tile_list = nullptr;
     if ((e = cudaMemsetAsync(Q.tally + 5, 0, 3 * sizeof(unsigned long long), st))) return e;
+    if ((e = cudaMemsetAsync(tile_info, 0, 2 * sizeof(unsigned long long), st))) return e;
     if constexpr (sizeof(R) == 4) {
         if (B2RT_OPT_MASKS && fuse_primary && primary_scan && W % 32 == 0 && !(a.flags & 128) &&
             S.n_box + S.n_loose + S.n_sphere <= 32) {
             masks = (unsigned *)(base + L.mask_off);
             tile_list = (int *)(base + L.mask_off + align256(((size_t)W * H / 32 + 1) * sizeof(unsigned)));
             primary_mask_kernel<<<(npix / 32 + 127) / 128, 128, 0, st>>>(S, make_cam<float>(cam), W, H, masks, Q.tally + 5);
-            tile_compact_kernel<<<1, 1024, 0, st>>>(masks, npix / 32, tile_list, Q.tally + 7);
+            tile_compact_kernel<<<1, 1024, 0, st>>>(masks, npix / 32, tile_list, tile_info);
         }
     }
     if (sort_rays) iota_kernel<<<g_simple, T, 0, st>>>((int)((size_t)npix * wave), iota);
@@ -233,7 +235,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
         PA.by_npix = FastDiv::make((unsigned)npix); PA.by_w = FastDiv::make((unsigned)W);
         PA.tiles_x = (W % 8 == 0 && H % 4 == 0) ? W / 8 : 0;
         PA.by_tiles = FastDiv::make((unsigned)(PA.tiles_x > 0 ? PA.tiles_x : 1));
-        PA.masks = masks; PA.tiles = tile_list; PA.n_tiles = Q.tally + 7;
+        PA.masks = masks; PA.tiles = tile_list; PA.n_tiles = tile_info;
         if ((e = cudaMemsetAsync(counts, 0, counts_bytes_wave, st))) return e;
         if ((e = cudaMemsetAsync(Q.clk, 0, (2 + (size_t)a.max_depth + 1) * sizeof(unsigned long long), st))) return e;
         if (!fuse_primary) {

@@ -45,11 +45,13 @@ struct PcgRng {                       // 32-bit PCG-RXS-M-XS stream, seeded by h
     static __device__ __forceinline__ uint64_t advance(uint64_t s) {
         return (uint64_t)((uint32_t)s * 747796405u + 2891336453u);
     }
-    template <typename R> static __device__ __forceinline__ R random(uint64_t s64) {
+    static __device__ __forceinline__ uint32_t word(uint64_t s64) {          // the full 32-bit output of the state
         uint32_t s = (uint32_t)s64;
         uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
-        w = (w >> 22u) ^ w;
-        return R(w >> 8) * R(1.0 / 16777216.0);
+        return (w >> 22u) ^ w;
+    }
+    template <typename R> static __device__ __forceinline__ R random(uint64_t s64) {
+        return R(word(s64) >> 8) * R(1.0 / 16777216.0);
     }
     static __device__ __forceinline__ uint32_t mix(uint32_t h) {
         h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
@@ -58,7 +60,8 @@ struct PcgRng {                       // 32-bit PCG-RXS-M-XS stream, seeded by h
     static __device__ __forceinline__ uint64_t seed(uint32_t pixel, uint64_t sample, uint64_t seed) {
         uint32_t h = mix(pixel * 0x9e3779b1u + (uint32_t)seed);
         h = mix(h ^ ((uint32_t)sample * 0x85ebca77u + (uint32_t)(seed >> 32)));
-        h = mix(h + (uint32_t)(sample >> 32) * 0xc2b2ae3du + 0x27d4eb2fu);
+        // sample indices beyond 2^32 get a third round (warp-uniform: never taken below 4 G samples per pixel)
+        if (sample >> 32) h = mix(h + (uint32_t)(sample >> 32) * 0xc2b2ae3du + 0x27d4eb2fu);
         return (uint64_t)h;
     }
 };
@@ -225,7 +228,8 @@ extend_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__res
         real4<R> a = ld_stream(ro + i), b = ld_stream(rd + i);
         Ray<R> r; r.o = xyz<R>(a); r.d = xyz<R>(b);
         Hit<R> h;
-        if (scan) scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
+        if ((int)unpack_u<R>(a.w) < 0) { h.t = R(1000000.0); h.prim = -1; h.a = h.b = R(0); }      // dead queue entry
+        else if (scan) scan_all<R, false, false>(S, r, R(0.001), R(1000000.0), h);
         else traverse<R, false, false>(S, s_top, r, R(0.001), R(1000000.0), h);
         st_stream(hit + i, Real4<R>::make(h.t, pack_int<R>((int64_t)h.prim), h.a, h.b));
     }
@@ -305,8 +309,11 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                     id = {rcp_(r.d.x), rcp_(r.d.y), rcp_(r.d.z)};
                     best.t = R(1000000.0); best.prim = -1; best.a = R(0); best.b = R(0);
                     stack[0] = kDone; sp = 1;
-                    ref = S.n_prims > 0 ? S.root : kDone;
-                    if (S.n_outside > 0) {                       // rectangles outside the hierarchy: leaves visited first
+                    // a dead entry (unused remainder of a producer warp's chunk, slot word -1) is no ray at all
+                    const bool dead_entry = (int)unpack_u<R>(a.w) < 0;
+                    ref = (S.n_prims > 0 && !dead_entry) ? S.root : kDone;
+                    if (dead_entry) pos = -1;
+                    if (S.n_outside > 0 && !dead_entry) {        // rectangles outside the hierarchy: leaves visited first
                         stack[sp++] = ref;
                         for (int p = S.n_outside - 1; p >= 1; --p) stack[sp++] = ~p;
                         ref = ~0;
@@ -367,6 +374,22 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
 // cuda_sample_hemisphere_cosine (:139-180)
 template <typename R, typename Rng>
 __device__ __forceinline__ V3<R> cos_hemisphere(V3<R> n, uint64_t &rng) {
+#ifndef B2RT_OPT_RNG16
+#define B2RT_OPT_RNG16 1           // 0: one generator step per random number in the float32 / PCG kernels as well
+#endif
+    if constexpr (sizeof(R) == 4 && B2RT_OPT_RNG16 && std::is_same<Rng, PcgRng>::value) {
+        // float32 production with the counter-based generator: cosine-weighted direction = normalize(n + s), s uniform
+        // on the unit sphere (exact; no tangent frame), both coordinates of s from ONE generator step (16 bits each,
+        // cell centres: unbiased for anything smoother than 2^-16).  ~35 instructions instead of ~64.
+        const uint32_t w = PcgRng::word(rng);
+        rng = PcgRng::advance(rng);
+        const float z = fmaf((float)(w >> 16), -2.0f / 65536.0f, 1.0f - 1.0f / 65536.0f);       // 1 - 2 (k + 0.5) / 65536
+        const float phi = fmaf((float)(w & 0xffffu), 6.2831853071795865f / 65536.0f, -3.14159265358979f + 3.14159265358979f / 65536.0f);
+        const float sr = sqrt_(fmaxf(fmaf(-z, z, 1.0f), 0.0f));
+        const float dx = fmaf(sr, __cosf(phi), n.x), dy = fmaf(sr, __sinf(phi), n.y), dz = z + n.z;
+        const float il = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-12f));
+        return {dx * il, dy * il, dz * il};
+    }
     R r1 = Rng::template random<R>(rng); rng = Rng::advance(rng);
     R r2 = Rng::template random<R>(rng); rng = Rng::advance(rng);
     R ct = sqrt_(r1), st = sqrt_(R(1) - r1);
@@ -433,6 +456,8 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
     V3<R> &thr = g.thr, &new_o = g.new_o, &new_d = g.new_d, &s_o = g.s_o, &s_d = g.s_d, &s_c = g.s_c;
     uint64_t &rng = g.rng;
     bool &alive = g.alive, &want_shadow = g.want_shadow;
+    constexpr bool RNG16 = B2RT_OPT_RNG16 && sizeof(R) == 4 && std::is_same<Rng, PcgRng>::value;
+    float choice16 = 0.f;
     if (FIRST) {                                                            // first touch of L[slot]
         R sky = h.prim < 0 ? R(0.1) : R(0);
         Q.L[slot] = Real4<R>::make(sky, sky, sky, R(0));
@@ -460,9 +485,18 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
         V3<R> po = sf.p + sf.n * R(0.001);
         if (S.n_lights > 0) {                                               // :265-304
             R nl = R(S.n_lights);
-            int li = (int)(Rng::template random<R>(rng) * nl);
-            if (li >= S.n_lights) li = S.n_lights - 1;
-            rng = Rng::advance(rng);
+            int li;
+            if constexpr (RNG16) {
+                // one generator step serves the light pick (low 16 bits) and the lobe choice below (high 16 bits)
+                const uint32_t w = PcgRng::word(rng);
+                rng = PcgRng::advance(rng);
+                li = (int)(((w & 0xffffu) * (uint32_t)S.n_lights) >> 16);
+                choice16 = fmaf((float)(w >> 16), 1.0f / 65536.0f, 0.5f / 65536.0f);
+            } else {
+                li = (int)(Rng::template random<R>(rng) * nl);
+                if (li >= S.n_lights) li = S.n_lights - 1;
+                rng = Rng::advance(rng);
+            }
             V3<R> l = xyz<R>(ldg4(reinterpret_cast<const real4<R> *>(S.lights) + li)) - sf.p;
             R dist = length(l);
             if (dist > R(0.001)) l = div3(l, dist);
@@ -505,8 +539,9 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
             else { rng = Rng::advance(rng); thr = div3(thr, p); }
         }
         if (go) {
-            R choice = Rng::template random<R>(rng);                        // :317-318
-            rng = Rng::advance(rng);
+            R choice;                                                       // :317-318
+            if (RNG16 && S.n_lights > 0) choice = R(choice16);
+            else { choice = Rng::template random<R>(rng); rng = Rng::advance(rng); }
             R dn = r.d.x * sf.n.x + r.d.y * sf.n.y + r.d.z * sf.n.z;
             V3<R> refl = {r.d.x - R(2) * dn * sf.n.x, r.d.y - R(2) * dn * sf.n.y, r.d.z - R(2) * dn * sf.n.z};
             new_o = po;
@@ -728,7 +763,10 @@ tile_compact_kernel(const unsigned *__restrict__ masks, int n_tiles, int *__rest
     }
     int pos = s_sum[t] - c;
     for (int i = lo; i < hi; ++i) if (masks[i] != 0u) tiles[pos++] = i;
-    if (t == 1023) *count = (unsigned long long)s_sum[1023];
+    if (t == 1023) {
+        const unsigned d = (unsigned)s_sum[1023];
+        count[0] = (unsigned long long)d;
+    }
 }
 
 template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fused into the first bounce
@@ -785,14 +823,18 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
     // tile-list mode (MODE 5 with candidate masks): item i = ((sample * non-empty tiles + tile index) * 32 + lane)
     const bool TILED = PLANAR && PRIMARY && B2RT_OPT_MASKS && B2RT_OPT_TILE_LIST && P.masks != nullptr;
-    const unsigned n_act = TILED ? (unsigned)(*P.n_tiles & 0xffffffffULL) : 1u;
+    const unsigned n_act = TILED ? (unsigned)(P.n_tiles[0] & 0xffffffffULL) : 1u;
+    // (sample, tile index) of this warp's item, stepped along with the grid-stride loop instead of divided out per item
+    unsigned t_s = 0, t_i = 0;
+    const unsigned t_step = (gridDim.x * blockDim.x) >> 5;
+    if (TILED) { const unsigned g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t_s = g0 / n_act; t_i = g0 - t_s * n_act; }
     int n = PRIMARY ? (TILED ? (int)n_act * 32 * P.spp_wave : P.W * P.H * P.spp_wave) : ray_count(Q, bounce);
     // ray statistics: every camera ray counts as answered, whether its tile was visited or not
     if (PRIMARY && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)(P.W * P.H * P.spp_wave);
     int n_round = (n + 31) & ~31;                // whole warps iterate together (ballots in warp_append2)
     unsigned n_culled = 0, n_tally = 0;          // n_tally: shaded hits (low 16 bits) | bounds-culled camera rays << 16
-    // small-scene kernels append through per-warp chunks (one tail atomic per ~5 iterations instead of one per iteration)
-    constexpr bool CHUNKED = B2RT_OPT_CHUNKED && PLANAR;
+    // queue appends go through per-warp chunks (one tail atomic per ~5 iterations instead of one per iteration)
+    constexpr bool CHUNKED = B2RT_OPT_CHUNKED != 0;
     __shared__ WarpCursor s_wc[8];
     WarpCursor *wc = s_wc + (threadIdx.x >> 5);
     if (CHUNKED && (threadIdx.x & 31) == 0) { wc->ray_cur = wc->ray_end = wc->sh_cur = wc->sh_end = 0; }
@@ -836,9 +878,8 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                     // sample-major like the untiled order: concurrently running warps touch neighbouring L[slot] lines.
                     // (Tile-major order — the warps of a CTA on the same tile, consecutive samples — put their L lines
                     // a multiple of npix * 16 B apart and ran bounce 0 AND bounce 1 ~60 % slower: profiles/r2e.)
-                    const unsigned g32 = (unsigned)i >> 5;
-                    s = (int)(g32 / n_act);
-                    const int tile = __ldg(P.tiles + (g32 - (unsigned)s * n_act));
+                    s = (int)t_s;
+                    const int tile = __ldg(P.tiles + t_i);
                     pix = tile * 32 + (i & 31);
                     mask = __ldg(P.masks + tile);
                 } else {
@@ -904,6 +945,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
             }
         }
         n_culled += g.culled ? 1u : 0u;
+        if (TILED) { t_i += t_step; while (t_i >= n_act) { t_i -= n_act; ++t_s; } }
         int si, ni;
         if constexpr (CHUNKED) warp_append_chunked(Q.counts + bounce + 1, wc, g.alive, g.want_shadow, ni, si);
         else warp_append2(Q.counts + bounce + 1, g.alive, g.want_shadow, ni, si);
@@ -927,7 +969,10 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         const int lane = threadIdx.x & 31;
         const int rc = wc->ray_cur, re = wc->ray_end, sc = wc->sh_cur, se = wc->sh_end;
 #pragma unroll 1
-        for (int k = rc + lane; k < re; k += 32) st_stream(no + k, Real4<R>::make(R(0), R(0), R(0), pack_int<R>(-1)));
+        for (int k = rc + lane; k < re; k += 32) {
+            st_stream(no + k, Real4<R>::make(R(0), R(0), R(0), pack_int<R>(-1)));
+            if ((WALK || MODE == 0) && Q.keys) Q.keys[k] = 0xffffffffu;          // dead entries sort to the end
+        }
 #pragma unroll 1
         for (int k = sc + lane; k < se; k += 32) st_stream(Q.so + k, Real4<R>::make(R(0), R(0), R(0), pack_int<R>(-1)));
         if (lane == 0 && (re - rc) + (se - sc) > 0)
