@@ -54,11 +54,11 @@ QUEUE_RECORD_BYTES = 48.0       # one ray-queue or shadow-queue record (3 float4
 COST = {"slab": 24.0, "triangle": 45.0, "sphere": 28.0, "rect": 33.0, "box_record": 42.0, "shade": 150.0, "camera": 21.0}
 # dram__bytes_read.sum + dram__bytes_write.sum from one `ncu --set full` capture of one 32-spp wave at 1080p
 # (profiles/, file named in NCU_SOURCE): bounce launches, shadow launches, accumulate
-NCU_SOURCE = "profiles/r1e_ncu_full_one_wave_32spp.csv"
+NCU_SOURCE = "profiles/r2_ncu_full_c2.csv"
 NCU_WAVE_PATHS = 1920 * 1080 * 32
-NCU_BOUNCE_BYTES_PER_WAVE = 13.075816e9
-NCU_SHADOW_BYTES_PER_WAVE = 1.471e9
-NCU_ACCUM_BYTES_PER_WAVE = 1.129566e9
+NCU_BOUNCE_BYTES_PER_WAVE = 12.981e9      # 8 bounce launches: 6.958 GB read + 6.023 GB written
+NCU_SHADOW_BYTES_PER_WAVE = 1.499e9       # 8 shadow launches
+NCU_ACCUM_BYTES_PER_WAVE = 0.593e9        # accumulate (tiles that see nothing are never written or read)
 NCU_TRAFFIC_BYTES_PER_LAUNCH = NCU_BOUNCE_BYTES_PER_WAVE / 8
 
 

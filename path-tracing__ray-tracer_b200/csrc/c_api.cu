@@ -189,7 +189,7 @@ int b2rt_render_path(const b2rt_scene *scene, const double *h_cam, int32_t width
                      uint64_t *d_counters, void *stream) {
     if (int r = check_scene(scene)) return r;
     if (max_depth < 1) return fail_msg("render_path: max_depth must be >= 1");
-    if ((long long)width * height * (long long)(spp_per_wave < 1 ? 1 : spp_per_wave) > 0x7fffffffLL)
+    if ((long long)width * height * (long long)(spp_per_wave < 1 ? 1 : spp_per_wave) > 0x7fffffffLL - (1LL << 22))
         return fail_msg("render_path: wave larger than 2^31 paths");
     b2rt::PathArgs a;
     a.width = width; a.height = height; a.spp_local = spp_local; a.spp_per_wave = spp_per_wave;

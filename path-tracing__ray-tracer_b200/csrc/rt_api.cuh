@@ -115,10 +115,11 @@ template <typename R> struct PathLayout {
         // per-bounce queue tails, unshadowed, culled + one ray-fetch counter per bounce (extend_walk_kernel)
         L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (3 * (size_t)max_depth + 18));
         // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
-        L.int_bytes = align256(n * sizeof(int));
+        const size_t nq = n + (size_t)kQueueSlack;           // queue tails include the dead chunk remainders
+        L.int_bytes = align256(nq * sizeof(int));
         L.cub_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, L.cub_bytes, (const unsigned *)nullptr, (unsigned *)nullptr,
-                                        (const int *)nullptr, (int *)nullptr, (int)n, 0, 30);
+                                        (const int *)nullptr, (int *)nullptr, (int)nq, 0, 30);
         L.cub_bytes = align256(L.cub_bytes);
         // camera-ray candidate masks: one word per 32-pixel tile (small scenes)
         L.mask_off = L.sort_off + 4 * L.int_bytes + L.cub_bytes;
@@ -225,7 +226,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
             tile_compact_kernel<<<1, 1024, 0, st>>>(masks, npix / 32, tile_list, tile_info);
         }
     }
-    if (sort_rays) iota_kernel<<<g_simple, T, 0, st>>>((int)((size_t)npix * wave), iota);
+    if (sort_rays) iota_kernel<<<g_simple, T, 0, st>>>((int)((size_t)npix * wave + kQueueSlack), iota);
     for (int done = 0; done < a.spp_local; done += wave) {
         int k = a.spp_local - done < wave ? a.spp_local - done : wave;
         unsigned long long launches = 0;
