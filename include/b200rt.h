@@ -74,7 +74,15 @@ extern "C" {
  * replaces the AoS float32 block of _prepare_scene_data / _prepare_light_data
  * (cuda_path_tracer.py:819-899,942-946).
  */
+#define B2RT_ABI_VERSION 2       /* layout of b2rt_scene below; bumped whenever a field is added, moved or re-interpreted */
+#define B2RT_SCAN_MAX_PRIMS 64   /* scenes up to this size scan all primitives for incoherent rays (scan_incoherent) */
+
 typedef struct b2rt_scene {
+    /* ABI guard: every entry point that takes a scene refuses one whose two first words differ from the library's own
+     * sizeof(b2rt_scene) / B2RT_ABI_VERSION (rc 3, text in b2rt_last_error), so a caller built against another header
+     * fails loudly instead of being read at wrong offsets. */
+    uint32_t struct_size;    /* = sizeof(b2rt_scene) */
+    uint32_t abi_version;    /* = B2RT_ABI_VERSION */
     int32_t precision;       /* element type of the real4 arrays below */
     int32_t semantics;       /* B2RT_SEM_* */
     int32_t n_rect, n_sphere, n_tri;
@@ -137,6 +145,37 @@ typedef struct b2rt_scene {
 } b2rt_scene;
 
 const char *b2rt_last_error(void);
+
+/* ---- scene preparation: the optional small-scene acceleration data, derived INSIDE the library ---------------------
+ * b2rt_scene's base streams (d_rect .. d_lights, d_prim_mat, d_mat, d_mat_tex) are all a caller has to fill.  The
+ * optional fields that make small scenes fast — scan_incoherent, d_scan_prims / n_scan_prims / n_scan_loose /
+ * n_scan_boxes (planar + box records), d_surface_records, d_occluder_hint, bounds_lo / bounds_hi — are derived from
+ * them by b2rt_scene_prepare (the reference has no counterpart: its cuda_scene_hit tests every primitive in turn,
+ * cuda_path_tracer.py:496-730).  Python's b200rt.packer keeps an independent numpy implementation of the same
+ * derivations; the CPU tests compare the two. */
+#define B2RT_PREPARE_NO_BOXES   1   /* planar records only (no three-slab box records) */
+#define B2RT_PREPARE_NO_SURFACE 2   /* no surface records: the bounce kernels use the generic shade / material streams */
+#define B2RT_PREPARE_NO_HINTS   4   /* no occluder hints */
+typedef struct b2rt_prepare_layout {   /* where b2rt_scene_prepare_host put what (byte offsets into its output buffer) */
+    size_t scan_offset, surface_offset, hint_offset;      /* (size_t)-1: not produced */
+    size_t bytes_used;
+    int32_t n_scan_prims, n_scan_loose, n_scan_boxes, scan_incoherent;
+    float bounds_lo[3], bounds_hi[3];
+} b2rt_prepare_layout;
+/* upper bound on the bytes b2rt_scene_prepare / _host write for a scene with these counts */
+int b2rt_scene_prepare_bytes(int32_t n_rect, int32_t n_sphere, int32_t n_tri, int32_t n_lights, size_t *h_bytes);
+/* Reads the float32 base streams of `scene` back from the device (a few KB: only scenes of <= B2RT_SCAN_MAX_PRIMS
+ * primitives get records), derives the records on the host, uploads them into d_buffer (caller-owned, at least
+ * b2rt_scene_prepare_bytes) and points the optional fields of `scene` at them.  Larger, float64 or CPU-semantics
+ * scenes get scan_incoherent / bounds set and nothing else.  Synchronises the stream. */
+int b2rt_scene_prepare(struct b2rt_scene *scene, void *d_buffer, size_t buffer_bytes, int32_t flags, void *stream);
+/* The same derivation on HOST copies of the float32 streams (layouts as documented at b2rt_scene) into a host buffer:
+ * for binders that pack on the host and upload everything in one copy, and for tests without a GPU. */
+int b2rt_scene_prepare_host(int32_t n_rect, int32_t n_sphere, int32_t n_tri, int32_t n_mat, int32_t n_lights,
+                            const float *h_rect, const float *h_sphere, const float *h_tri, const float *h_shade,
+                            const float *h_mat, const int32_t *h_prim_mat, const int32_t *h_mat_tex,
+                            const float *h_lights, int32_t flags, void *h_out, size_t out_bytes,
+                            b2rt_prepare_layout *h_layout);
 int b2rt_version(void);
 /* h_out[0..5] = SM count, max smem per block (opt-in), L2 bytes, SM clock kHz, cc major, cc minor */
 int b2rt_device_info(int device, int64_t *h_out);
@@ -236,6 +275,13 @@ int b2rt_reduce_resolve(const void *const *h_peer_accum, int32_t n_peers, int32_
 /* ---- texture upload helper (replaces the RGB flattening of _prepare_texture_data, cuda_path_tracer.py:901-932) */
 /* d_rgb: n_texels packed RGB8 triples (4-byte aligned) -> d_rgbx: n_texels RGBX8 words (16-byte aligned) */
 int b2rt_expand_rgb8(const uint8_t *d_rgb, int64_t n_texels, uint32_t *d_rgbx, void *stream);
+
+/* ---- checked build (the compute-sanitizer substitute) ------------------------------------------------------------------
+ * A library compiled with -DB2RT_CHECK=1 bounds-checks every traversal-stack push and every queue append inside the
+ * kernels; violations are counted and the offending write is dropped (the context stays usable).  b2rt_check_read
+ * returns and clears the counts of the current device (both 0 in a normal build, where b2rt_check_enabled() is 0). */
+int b2rt_check_enabled(void);
+int b2rt_check_read(uint64_t *h_stack_overflows, uint64_t *h_queue_overruns);
 
 /* ---- measurement helpers (no reference counterpart: the reference times render() with time.time(),
  *      main.py:89-91) ----------------------------------------------------------------------------------- */

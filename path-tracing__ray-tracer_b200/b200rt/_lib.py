@@ -18,12 +18,30 @@ EXPORTS = [
     "b2rt_primary_hits", "b2rt_trace_rays", "b2rt_render_whitted_cpu", "b2rt_render_whitted_texture",
     "b2rt_path_workspace_bytes", "b2rt_render_path", "b2rt_resolve",
     "b2rt_profile_enable", "b2rt_profile_read", "b2rt_fp32_peak", "b2rt_reduce_resolve", "b2rt_expand_rgb8",
+    "b2rt_scene_prepare_bytes", "b2rt_scene_prepare", "b2rt_scene_prepare_host",
+    "b2rt_check_enabled", "b2rt_check_read",
 ]
+ABI_VERSION = 2
+
+
+class PrepareLayout(C.Structure):
+    """``struct b2rt_prepare_layout`` (include/b200rt.h)."""
+    _fields_ = [("scan_offset", C.c_size_t), ("surface_offset", C.c_size_t), ("hint_offset", C.c_size_t),
+                ("bytes_used", C.c_size_t), ("n_scan_prims", C.c_int32), ("n_scan_loose", C.c_int32),
+                ("n_scan_boxes", C.c_int32), ("scan_incoherent", C.c_int32),
+                ("bounds_lo", C.c_float * 3), ("bounds_hi", C.c_float * 3)]
+
+
+def new_scene_struct():
+    s = SceneStruct()
+    s.struct_size, s.abi_version = C.sizeof(SceneStruct), ABI_VERSION
+    return s
 
 
 class SceneStruct(C.Structure):
     """``struct b2rt_scene`` (include/b200rt.h)."""
     _fields_ = [
+        ("struct_size", C.c_uint32), ("abi_version", C.c_uint32),
         ("precision", C.c_int32), ("semantics", C.c_int32),
         ("n_rect", C.c_int32), ("n_sphere", C.c_int32), ("n_tri", C.c_int32),
         ("n_mat", C.c_int32), ("n_tex", C.c_int32), ("n_lights", C.c_int32),
@@ -74,6 +92,11 @@ def load():
     lib.b2rt_fp32_peak.argtypes = [i32, C.POINTER(dbl), vp]
     lib.b2rt_reduce_resolve.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, dbl, i32, vp, vp, vp]
     lib.b2rt_expand_rgb8.argtypes = [vp, i64, vp, vp]
+    lib.b2rt_check_read.argtypes = [C.POINTER(u64), C.POINTER(u64)]
+    lib.b2rt_scene_prepare_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
+    lib.b2rt_scene_prepare.argtypes = [SP, vp, sz, i32, vp]
+    lib.b2rt_scene_prepare_host.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, sz,
+                                            C.POINTER(PrepareLayout)]
     for name in EXPORTS:
         if name not in ("b2rt_last_error",):
             getattr(lib, name).restype = C.c_int

@@ -7,6 +7,7 @@ Objects:
   rt_f64.o  float64 parity kernels, same source   (-fmad=false: the reference never contracts a*b+c)
   lbvh.o    LBVH builder (Morton + CUB radix sort + Karras hierarchy + refit)
   c_api.o   extern "C" surface of include/b200rt.h
+  scene_prepare.o  small-scene record derivation (host C++; b2rt_scene_prepare)
 """
 from __future__ import annotations
 
@@ -27,7 +28,13 @@ UNITS = [
     ("rt_f64.cu", ["-fmad=false"]),
     ("lbvh.cu", []),
     ("c_api.cu", []),
+    ("scene_prepare.cu", []),
 ]
+
+
+def variant_path(name: str) -> str:
+    """In-tree path of a named build variant (``libb200rt_<name>.so`` next to the default library)."""
+    return os.path.join(PKG_DIR, "b200rt", f"libb200rt_{name}.so")
 
 
 def nvcc() -> str:

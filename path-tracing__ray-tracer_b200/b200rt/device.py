@@ -99,7 +99,10 @@ class DeviceScene:
                  top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
                  scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True, ray_sort_min_prims: int = 4096,
                  scan_boxes: bool = True, surface_records: bool = True, rects_outside: bool = True,
-                 lbvh_rotations: bool = True):
+                 lbvh_rotations: bool = True, prepare: str = "library"):
+        """``prepare``: who derives the small-scene records (scan / box / surface records, occluder hints, bounds) —
+        ``"library"`` = ``b2rt_scene_prepare_host`` inside ``libb200rt.so`` (what any C-ABI binder gets), ``"numpy"`` =
+        the independent implementation in ``packer.py`` (kept as the cross-check; the CPU tests compare the two)."""
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.packed = packed
@@ -120,14 +123,33 @@ class DeviceScene:
                 blob.add("tex_info", packed.tex_info if packed.n_tex else np.zeros((1, 4), np.int32))
             self.scan_host = self.occluder_hint_host = None
             scan_ok = 0 < packed.n_prims <= scan_max_prims
+            self.prepared_by = None
             if scan_ok and precision == _lib.P_F32 and packed.semantics == 0:
-                self.scan_host, self.occluder_hint_host, self.n_scan_loose, self.scan_boxes_host = \
-                    _small_scene_records(packed, occluder_hints, scan_boxes)
-                if self.scan_host is not None:
-                    from .packer import build_surface_records
-                    blob.add("scan", np.concatenate([self.scan_host, self.scan_boxes_host]))
-                    if surface_records:
-                        blob.add("surf", build_surface_records(packed))
+                if prepare == "library" and scan_max_prims <= 64:
+                    lay, host = _library_records(self.lib, packed, occluder_hints, scan_boxes, surface_records)
+                    if lay is not None and lay.scan_offset != _NONE:
+                        nrec = lay.n_scan_prims + lay.n_scan_boxes
+                        rec = np.frombuffer(host, dtype=np.float32, count=16 * nrec, offset=lay.scan_offset).reshape(-1, 4)
+                        self.scan_host = rec[:4 * lay.n_scan_prims]
+                        self.scan_boxes_host = rec[4 * lay.n_scan_prims:]
+                        self.n_scan_loose = int(lay.n_scan_loose)
+                        blob.add("scan", rec)
+                        if lay.surface_offset != _NONE:
+                            blob.add("surf", np.frombuffer(host, dtype=np.float32, count=20 * packed.n_prims,
+                                                           offset=lay.surface_offset).reshape(-1, 4))
+                        if lay.hint_offset != _NONE:
+                            self.occluder_hint_host = np.frombuffer(host, dtype=np.int32, count=packed.lights.shape[0],
+                                                                    offset=lay.hint_offset).copy()
+                        self.prepared_by = "library"
+                else:
+                    self.scan_host, self.occluder_hint_host, self.n_scan_loose, self.scan_boxes_host = \
+                        _small_scene_records(packed, occluder_hints, scan_boxes)
+                    if self.scan_host is not None:
+                        from .packer import build_surface_records
+                        blob.add("scan", np.concatenate([self.scan_host, self.scan_boxes_host]))
+                        if surface_records:
+                            blob.add("surf", build_surface_records(packed))
+                        self.prepared_by = "numpy"
             elif (not scan_ok and precision == _lib.P_F32 and packed.semantics == 0 and occluder_hints
                   and 0 < packed.n_rect <= 64 and packed.n_sphere <= 64 and 0 < packed.lights.shape[0] <= 4096):
                 from .packer import build_occluder_hints, rect_scan_records
@@ -167,7 +189,7 @@ class DeviceScene:
                                                 (1 if self.rects_outside else 0) | (0 if lbvh_rotations else 2)),
                        "b2rt_lbvh_build")
             self.n_top, self.root, self.n_internal = int(meta[0]), int(meta[1]), int(meta[2])
-        s = _lib.SceneStruct()
+        s = _lib.new_scene_struct()
         s.precision, s.semantics = precision, packed.semantics
         s.n_rect, s.n_sphere, s.n_tri = packed.n_rect, packed.n_sphere, packed.n_tri
         s.n_mat, s.n_tex, s.n_lights = packed.n_mat, packed.n_tex, packed.lights.shape[0]
@@ -203,6 +225,35 @@ class DeviceScene:
 
 
 _small_cache: dict = {}
+_NONE = (1 << 64) - 1          # (size_t)-1: "not produced" in b2rt_prepare_layout
+
+
+def _library_records(lib, packed: PackedScene, want_hints: bool, want_boxes: bool, want_surface: bool):
+    """Small-scene records from ``b2rt_scene_prepare_host`` (host C++ inside the library), cached on the bytes of the
+    packed streams like the numpy path -> (layout, host buffer)."""
+    import hashlib
+    f32 = {k: np.ascontiguousarray(getattr(packed, k), dtype=np.float32) for k in ("rect", "sphere", "tri", "shade", "mat", "lights")}
+    pm, mt = np.ascontiguousarray(packed.prim_mat, dtype=np.int32), np.ascontiguousarray(packed.mat_tex, dtype=np.int32)
+    h = hashlib.blake2b(digest_size=16)
+    for a in (*f32.values(), pm, mt):
+        h.update(a.tobytes())
+    key = ("lib", h.hexdigest(), bool(want_hints), bool(want_boxes), bool(want_surface))
+    if key not in _small_cache:
+        need = C.c_size_t(0)
+        n_lights = int(packed.lights.shape[0])
+        lib.b2rt_scene_prepare_bytes(packed.n_rect, packed.n_sphere, packed.n_tri, n_lights, C.byref(need))
+        out = np.zeros(need.value, dtype=np.uint8)
+        lay = _lib.PrepareLayout()
+        flags = (0 if want_boxes else 1) | (0 if want_surface else 2) | (0 if want_hints else 4)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(lib.b2rt_scene_prepare_host(packed.n_rect, packed.n_sphere, packed.n_tri, packed.n_mat, n_lights,
+                                               ptr(f32["rect"]), ptr(f32["sphere"]), ptr(f32["tri"]), ptr(f32["shade"]),
+                                               ptr(f32["mat"]), ptr(pm), ptr(mt), ptr(f32["lights"]), flags, ptr(out),
+                                               out.nbytes, C.byref(lay)), "b2rt_scene_prepare_host")
+        _small_cache[key] = (lay, out)
+        if len(_small_cache) > 64:
+            _small_cache.pop(next(iter(_small_cache)))
+    return _small_cache[key]
 
 
 def _small_scene_records(packed: PackedScene, want_hints: bool, want_boxes: bool = True):

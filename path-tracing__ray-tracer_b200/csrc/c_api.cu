@@ -1,5 +1,6 @@
 // c_api.cu — the extern "C" surface declared in include/b200rt.h.
 #include <cuda_runtime.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -22,6 +23,17 @@ int fail_msg(const char *msg) {
     return 2;
 }
 inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+}  // namespace
+namespace b2rt {
+int set_error(int code, const char *fmt, ...) {          // used by the other translation units (scene_prepare.cu)
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace b2rt
+namespace {
 
 #define DISPATCH(scene_precision, call_f32, call_f64)                                   \
     ((scene_precision) == B2RT_PRECISION_F64 ? (call_f64) : (call_f32))
@@ -78,6 +90,26 @@ void prof_end(cudaStream_t st) {
 }
 }  // namespace b2rt
 
+// ---- B2RT_CHECK: in-kernel bounds checks counted into a library-owned device word (one per device) -------------------
+#ifndef B2RT_CHECK
+#define B2RT_CHECK 0
+#endif
+namespace b2rt {
+unsigned long long *check_counter() {
+#if B2RT_CHECK
+    static unsigned long long *ptr[64] = {nullptr};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ptr[dev] && cudaMalloc(&ptr[dev], sizeof(unsigned long long)) == cudaSuccess) cudaMemset(ptr[dev], 0, sizeof(unsigned long long));
+    return ptr[dev];
+#else
+    return nullptr;
+#endif
+}
+}  // namespace b2rt
+
 static __global__ void fp32_peak_kernel(float *out, int iters, float a, float b) {
     float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
     for (int i = 0; i < iters; ++i) {
@@ -91,7 +123,7 @@ static __global__ void fp32_peak_kernel(float *out, int iters, float a, float b)
 extern "C" {
 
 const char *b2rt_last_error(void) { return g_err; }
-int b2rt_version(void) { return 100; }
+int b2rt_version(void) { return 200 + B2RT_ABI_VERSION; }
 
 int b2rt_device_info(int device, int64_t *h_out) {
     cudaDeviceProp p;
@@ -129,6 +161,12 @@ int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri, const void 
 
 static int check_scene(const b2rt_scene *s) {
     if (!s) return fail_msg("scene is NULL");
+    if (s->struct_size != sizeof(b2rt_scene) || s->abi_version != B2RT_ABI_VERSION) {
+        snprintf(g_err, sizeof g_err, "b2rt_scene ABI mismatch: caller has struct_size %u / abi_version %u, library has %zu / %d "
+                                      "(set both from the header the caller was built against)",
+                 s->struct_size, s->abi_version, sizeof(b2rt_scene), B2RT_ABI_VERSION);
+        return 3;
+    }
     if (s->precision != B2RT_PRECISION_F32 && s->precision != B2RT_PRECISION_F64) return fail_msg("bad precision");
     if (s->n_bvh_top < 0 || s->n_bvh_top > b2rt::kTopMax) return fail_msg("n_bvh_top out of range");
     return 0;
@@ -221,6 +259,21 @@ int b2rt_expand_rgb8(const uint8_t *d_rgb, int64_t n_texels, uint32_t *d_rgbx, v
     if (((size_t)d_rgb & 3) || ((size_t)d_rgbx & 15)) return fail_msg("expand_rgb8: d_rgb must be 4-byte, d_rgbx 16-byte aligned");
     cudaError_t e = b2rt::expand_rgb8(d_rgb, n_texels, d_rgbx, S(stream));
     return e ? fail("b2rt_expand_rgb8", e) : 0;
+}
+
+int b2rt_check_enabled(void) { return B2RT_CHECK ? 1 : 0; }
+
+int b2rt_check_read(uint64_t *h_stack_overflows, uint64_t *h_queue_overruns) {
+    *h_stack_overflows = *h_queue_overruns = 0;
+    unsigned long long *p = b2rt::check_counter();
+    if (!p) return 0;
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpy(&v, p, sizeof v, cudaMemcpyDeviceToHost);        // synchronises with the kernels before it
+    if (!e) e = cudaMemset(p, 0, sizeof v);
+    if (e) return fail("b2rt_check_read", e);
+    *h_stack_overflows = v & 0xffffffffULL;
+    *h_queue_overruns = v >> 32;
+    return 0;
 }
 
 int b2rt_profile_enable(int32_t on) {

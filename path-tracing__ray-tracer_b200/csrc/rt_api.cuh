@@ -38,6 +38,7 @@ template <typename R>
 cudaError_t Api<R>::primary_hits(const b2rt_scene *s, const double *cam, int W, int H, double du, double dv,
                                  double t_min, double t_max, int use_bvh, int *ids, double *tt, cudaStream_t st) {
     SceneDev S = make_scene_dev(s);
+    S.check = check_counter();
     Cam<R> c = make_cam<R>(cam);
     int n = W * H, T = 128;
     if (cudaError_t e = opt_in_smem((const void *)primary_hits_kernel<R, true>, smem_top_bytes(S))) return e;
@@ -53,6 +54,7 @@ template <typename R>
 cudaError_t Api<R>::trace_rays(const b2rt_scene *s, int n, const double *o, const double *d, double t_min, double t_max,
                                int any_hit, int use_bvh, int *ids, double *rec, cudaStream_t st) {
     SceneDev S = make_scene_dev(s);
+    S.check = check_counter();
     int T = 128;
     if (n <= 0) return cudaSuccess;
     const size_t sm = use_bvh == 2 ? smem_scan_bytes(S) + 64 : smem_top_bytes(S);
@@ -70,6 +72,7 @@ cudaError_t Api<R>::whitted_cpu(const b2rt_scene *s, const double *cam, int W, i
                                 int max_depth, const double *ambient, const double *light_color, double *rgb,
                                 cudaStream_t st) {
     SceneDev S = make_scene_dev(s);
+    S.check = check_counter();
     Cam<R> c = make_cam<R>(cam);
     V3<R> amb = {R(ambient[0]), R(ambient[1]), R(ambient[2])};
     V3<R> lc = {R(light_color[0]), R(light_color[1]), R(light_color[2])};
@@ -83,6 +86,7 @@ template <typename R>
 cudaError_t Api<R>::whitted_texture(const b2rt_scene *s, const double *cam, int W, int H, int spp, int max_depth,
                                     double *rgb, uint8_t *u8, cudaStream_t st) {
     SceneDev S = make_scene_dev(s);
+    S.check = check_counter();
     Cam<R> c = make_cam<R>(cam);
     int n = W * H, T = 128;
     if (sizeof(R) == 4 && S.scan_incoherent && S.n_scan > 0 && S.surf)
@@ -135,6 +139,7 @@ template <typename R> size_t Api<R>::path_workspace_bytes(int W, int H, int spp_
 template <typename R, typename Rng>
 cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathArgs &a, cudaStream_t st) {
     SceneDev S = make_scene_dev(s);
+    S.check = check_counter();
     Cam<R> c = make_cam<R>(cam);
     const int W = a.width, H = a.height, npix = W * H;
     int wave = a.spp_per_wave < 1 ? 1 : a.spp_per_wave;
@@ -164,6 +169,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     int *iota = (int *)(base + L.sort_off + 2 * L.int_bytes), *perm = (int *)(base + L.sort_off + 3 * L.int_bytes);
     void *cub_tmp = base + L.sort_off + 4 * L.int_bytes;
     Q.keys = sort_rays ? keys : nullptr;
+    Q.capacity = (int)(L.stream_bytes / sizeof(real4<R>));
     Q.perm = nullptr;
 
     const size_t smem = smem_top_bytes(S);

@@ -27,6 +27,9 @@ struct PathArgs {
     unsigned long long *counters;
 };
 
+// B2RT_CHECK builds: the library-owned violation counter of the current device (nullptr in normal builds)
+unsigned long long *check_counter();
+
 // float32-only helpers (rt_f32.cu)
 cudaError_t reduce_resolve_f32(const void *const *peer_accum, int n_peers, int W, int H, int row0, int row1, double spp,
                                int tonemap, uint8_t *root_u8, void *root_sum, cudaStream_t st);

@@ -81,6 +81,7 @@ template <typename R> struct PathQueues {
     unsigned long long *tally;             // [8] bounds-culled camera rays, shaded hits, walk box / leaf steps, sky records
     unsigned *keys;                        // sort key of every ray appended to the next queue (or nullptr)
     const int *perm;                       // permutation the current queue is read through (or nullptr)
+    int capacity;                          // entries per queue stream (B2RT_CHECK builds verify every append against it)
 };
 
 // Ray-reordering key.  Layout 2 (default): 2 bits per direction component (6 bits) above a 24-bit Morton code of
@@ -314,8 +315,8 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                     ref = (S.n_prims > 0 && !dead_entry) ? S.root : kDone;
                     if (dead_entry) pos = -1;
                     if (S.n_outside > 0 && !dead_entry) {        // rectangles outside the hierarchy: leaves visited first
-                        stack[sp++] = ref;
-                        for (int p = S.n_outside - 1; p >= 1; --p) stack[sp++] = ~p;
+                        B2RT_PUSH(S, stack, sp, ref);
+                        for (int p = S.n_outside - 1; p >= 1; --p) B2RT_PUSH(S, stack, sp, ~p);
                         ref = ~0;
                     }
                 }
@@ -354,7 +355,7 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                 const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
                 if (hl && hr) {
                     const bool swap = tr < tl;
-                    stack[sp++] = swap ? cl : cr;
+                    B2RT_PUSH(S, stack, sp, swap ? cl : cr);
                     ref = swap ? cr : cl;
                 } else if (hl) ref = cl;
                 else if (hr) ref = cr;
@@ -949,6 +950,12 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         int si, ni;
         if constexpr (CHUNKED) warp_append_chunked(Q.counts + bounce + 1, wc, g.alive, g.want_shadow, ni, si);
         else warp_append2(Q.counts + bounce + 1, g.alive, g.want_shadow, ni, si);
+        if (B2RT_CHECK) {                        // queue overrun: counted (high word), the append is dropped
+            if ((g.want_shadow && si >= Q.capacity) || (g.alive && ni >= Q.capacity)) {
+                if (S.check) atomicAdd(S.check, 1ULL << 32);
+                g.want_shadow = g.alive = false;
+            }
+        }
         if (g.want_shadow) {
             // bit 31 of the slot word marks a pre-resolved record (sky term of an escaping path: nothing to trace)
             const unsigned slot_word = (unsigned)slot | (g.light < 0 ? 0x80000000u : 0u);

@@ -28,7 +28,17 @@ namespace b2rt {
 #ifndef B2RT_BVH_MIN_BLOCKS
 #define B2RT_BVH_MIN_BLOCKS 4         // ... for the float32 LBVH-walk bounce kernels (measured 6729 vs 6600 Mpaths/s with 3)
 #endif
-constexpr int kStackDepth = 64;
+// B2RT_CHECK build (the compute-sanitizer substitute: this pool refuses compute-sanitizer): every traversal-stack push and
+// every queue append is bounds-checked in the kernel; a violation is COUNTED (SceneDev.check: stack overflows in the low
+// word, queue overruns in the high word) and the offending write is skipped, so the context survives and the host can
+// assert on b2rt_check_read().  B2RT_STACK_DEPTH shrinks the stack to provoke the check in the negative test.
+#ifndef B2RT_CHECK
+#define B2RT_CHECK 0
+#endif
+#ifndef B2RT_STACK_DEPTH
+#define B2RT_STACK_DEPTH 64
+#endif
+constexpr int kStackDepth = B2RT_STACK_DEPTH;
 constexpr int kScanUnroll = B2RT_SCAN_UNROLL;       // LBVH depth bound: 30 Morton bits + log2(duplicates)
 
 struct SceneDev {
@@ -49,6 +59,7 @@ struct SceneDev {
     const float4 *surf;                // per-primitive shading records of small float32 scenes (or nullptr)
     float sort_inv;                    // 0.5 / ray_sort_extent, or 0 when ray sorting is off
     float blo[3], bhi[3];              // padded scene bounds (blo > bhi: unknown)
+    unsigned long long *check;         // B2RT_CHECK builds: violation counter (library-owned), else nullptr
 };
 
 inline SceneDev make_scene_dev(const b2rt_scene *s) {
@@ -73,12 +84,20 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.occl_hint = s->precision == B2RT_PRECISION_F32 ? s->d_occluder_hint : nullptr;
     d.surf = s->precision == B2RT_PRECISION_F32 ? reinterpret_cast<const float4 *>(s->d_surface_records) : nullptr;
     for (int k = 0; k < 3; ++k) { d.blo[k] = s->bounds_lo[k]; d.bhi[k] = s->bounds_hi[k]; }
+    d.check = nullptr;
     d.sort_inv = (s->ray_sort_extent > 0.f && !s->scan_incoherent) ? 0.5f / s->ray_sort_extent : 0.f;
     return d;
 }
 
 // closest-hit record: a/b are (u_hit, v_hit) in world units for a rectangle, the barycentrics
 // (u, v) for a triangle, unused for a sphere
+// bounds-checked traversal-stack push (plain store unless B2RT_CHECK)
+#define B2RT_PUSH(S_, stack_, sp_, v_)                                                              \
+    do {                                                                                            \
+        if (B2RT_CHECK && (sp_) >= kStackDepth) { if ((S_).check) atomicAdd((S_).check, 1ULL); }    \
+        else (stack_)[(sp_)++] = (v_);                                                              \
+    } while (0)
+
 template <typename R> struct Hit {
     R t, a, b;
     int prim;
@@ -256,8 +275,8 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
     int sp = 1;
     int ref = S.root;
     if (S.n_outside > 0) {                                       // see the if-if variant below
-        stack[sp++] = S.root;
-        for (int p = S.n_outside - 1; p >= 1; --p) stack[sp++] = ~p;
+        B2RT_PUSH(S, stack, sp, S.root);
+        for (int p = S.n_outside - 1; p >= 1; --p) B2RT_PUSH(S, stack, sp, ~p);
         ref = ~0;
     }
     while (ref != kDone) {
@@ -276,7 +295,7 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
             int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
             if (hl && hr) {
                 bool swap = tr < tl;
-                stack[sp++] = swap ? cl : cr;
+                B2RT_PUSH(S, stack, sp, swap ? cl : cr);
                 ref = swap ? cr : cl;
             } else if (hl) {
                 ref = cl;
@@ -302,8 +321,8 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
     // rectangles kept outside the hierarchy (B2RT_LBVH_RECTS_OUTSIDE) are visited FIRST, as leaves stacked above the
     // root, so a wall hit already bounds the walk (no second inlined copy of the primitive tests: that cost 10 %)
     if (S.n_outside > 0) {
-        stack[sp++] = S.root;
-        for (int p = S.n_outside - 1; p >= 1; --p) stack[sp++] = ~p;
+        B2RT_PUSH(S, stack, sp, S.root);
+        for (int p = S.n_outside - 1; p >= 1; --p) B2RT_PUSH(S, stack, sp, ~p);
         ref = ~0;
     }
     while (true) {
@@ -322,7 +341,7 @@ __device__ __forceinline__ bool traverse(const SceneDev &S, const float4 *s_top,
             int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
             if (hl && hr) {
                 bool swap = tr < tl;
-                stack[sp++] = swap ? cl : cr;
+                B2RT_PUSH(S, stack, sp, swap ? cl : cr);
                 ref = swap ? cr : cl;
             } else if (hl) {
                 ref = cl;

@@ -376,3 +376,77 @@ def test_scene_add_mesh_and_add_obj(tmp_path):
     T = pk.tri.reshape(-1, 3, 4)
     assert np.allclose(T[2, 0, :3], [0, 0, 2]) and np.allclose(T[2, 1, :3], [2, 0, 0])       # scaled OBJ triangle
     assert pk.order[1].tolist() == [1, 0] and pk.order[3].tolist() == [2, 0]                  # (object index, face index)
+
+
+# ------------------------------------------------------------------------------------ library-side scene preparation
+def _prepare_both(packed):
+    """(numpy records, library records) for one packed scene: (planar, n_loose, boxes, surface, hints, bounds)."""
+    import ctypes as C
+    from b200rt import _lib, device
+    from b200rt.packer import build_surface_records
+    rec, hints, n_loose, boxes = device._small_scene_records(packed, True, True)
+    ref = (rec, n_loose, boxes, build_surface_records(packed), hints, packed.bounds())
+    lay, host = device._library_records(_lib.load(), packed, True, True, True)
+    nrec = lay.n_scan_prims + lay.n_scan_boxes
+    allrec = np.frombuffer(host, dtype=np.float32, count=16 * nrec, offset=lay.scan_offset).reshape(-1, 4)
+    got = (allrec[:4 * lay.n_scan_prims], int(lay.n_scan_loose), allrec[4 * lay.n_scan_prims:],
+           np.frombuffer(host, dtype=np.float32, count=20 * packed.n_prims, offset=lay.surface_offset).reshape(-1, 4),
+           np.frombuffer(host, dtype=np.int32, count=packed.lights.shape[0], offset=lay.hint_offset),
+           (np.array(lay.bounds_lo[:]), np.array(lay.bounds_hi[:])))
+    return ref, got
+
+
+def _assert_records_equal(a, b, bit_cols):
+    """float columns to float32 rounding, bit-packed columns exactly."""
+    a, b = np.asarray(a, np.float32).reshape(-1, 4, 4), np.asarray(b, np.float32).reshape(-1, 4, 4)
+    assert a.shape == b.shape
+    ai, bi = a.view(np.int32), b.view(np.int32)
+    mask = np.zeros((4, 4), bool)
+    for r, c in bit_cols:
+        mask[r, c] = True
+    assert np.array_equal(ai[:, mask], bi[:, mask])
+    assert np.allclose(a[:, ~mask], b[:, ~mask], rtol=2e-6, atol=1e-6)
+
+
+def test_library_scene_prepare_matches_the_numpy_packer(cornell):
+    """b2rt_scene_prepare_host (host C++ inside libb200rt.so: what a C-ABI binder gets) derives the same planar / box /
+    surface records, bounds and occluder hints as the independent numpy implementation in b200rt.packer."""
+    from b200rt import packer
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import random_scenes as RS
+    scenes = [cornell[0]] + [RS.make_scene(RS.local_api(), s)[0] for s in (11, 12, 13)]
+    for i, scene in enumerate(scenes):
+        pk = packer.pack_scene(scene, "numba")
+        ref, got = _prepare_both(pk)
+        _assert_records_equal(ref[0], got[0], [(3, 2), (3, 3)])                      # planar: kind | idA, idB
+        assert ref[1] == got[1]
+        _assert_records_equal(ref[2], got[2], [(3, 0), (3, 1), (3, 2), (3, 3)])      # boxes: face codes, flags
+        s_ref, s_got = np.asarray(ref[3], np.float32).reshape(-1, 5, 4), got[3].reshape(-1, 5, 4)
+        assert np.array_equal(s_ref.view(np.int32)[:, 3:, 3], s_got.view(np.int32)[:, 3:, 3])      # texture id, flags
+        assert np.allclose(s_ref[:, :3], s_got[:, :3], rtol=1e-6, atol=1e-7) and np.allclose(s_ref[:, 3:, :3], s_got[:, 3:, :3], rtol=1e-6, atol=1e-7)
+        assert np.allclose(ref[5][0], got[5][0], rtol=1e-6) and np.allclose(ref[5][1], got[5][1], rtol=1e-6)
+        if i == 0:
+            # Cornell: three boxes (walls, two cubes), the canvas loose, every light sample shadowed by the ceiling record
+            assert got[2].shape[0] // 4 == 3 and got[1] == 1
+            assert np.array_equal(ref[4], got[4]) and len(set(got[4].tolist())) == 1
+
+
+def test_scene_struct_carries_size_and_abi_version():
+    """b2rt_scene starts with struct_size / abi_version; the ctypes mirror has the size the header's struct has."""
+    import ctypes as C
+    import re
+    from b200rt import _lib
+    s = _lib.new_scene_struct()
+    assert s.struct_size == C.sizeof(_lib.SceneStruct) and s.abi_version == _lib.ABI_VERSION
+    hdr = open(os.path.join(ROOT, "include", "b200rt.h")).read()
+    assert int(re.search(r"#define B2RT_ABI_VERSION (\d+)", hdr).group(1)) == _lib.ABI_VERSION
+    # compile the header with the host compiler and compare sizeof / the offset of the last field
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "b200rt.h"\n'
+                             'int main(void){printf("%zu %zu %zu", sizeof(b2rt_scene), offsetof(b2rt_scene, bounds_hi), sizeof(b2rt_prepare_layout));return 0;}')
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", os.path.join(d, "t")], check=True)
+        size, off, lay = (int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True).stdout.split())
+    assert size == C.sizeof(_lib.SceneStruct) and off == _lib.SceneStruct.bounds_hi.offset
+    assert lay == C.sizeof(_lib.PrepareLayout)
