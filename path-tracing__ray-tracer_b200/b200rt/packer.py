@@ -103,6 +103,33 @@ def texture_paths_sorted(scene) -> List[str]:
     return sorted(seen)
 
 
+def scene_signature(scene) -> tuple:
+    """Every value ``pack_scene`` reads from ``scene`` as one hashable tuple (the cache key of the renderers'
+    packed-scene cache): object kinds and all their float fields, materials, texture paths, lights, light colour and
+    ambient.  Meshes contribute the identity, shape and a strided fingerprint of their arrays."""
+    sig = []
+    for o in scene.objects:
+        k, m = kind_of(o), o.material
+        t = getattr(m, "texture", None)
+        ms = (m.color.x, m.color.y, m.color.z, m.diffuse, m.specular, m.reflective, getattr(m, "refractive", 0.0),
+              getattr(m, "ior", 1.0), getattr(t, "path", None) if t is not None else None)
+        if k == "plane":
+            sig.append((0, *_v(o.anchor), *_v(o.normal), *_v(o.u_dir), *_v(o.v_dir), o.u_len, o.v_len,
+                        *(_v(o.u_unit) if hasattr(o, "u_unit") else ()), getattr(o, "u_extent", None), getattr(o, "v_extent", None), ms))
+        elif k == "sphere":
+            sig.append((1, *_v(o.center), o.radius, ms))
+        elif k == "triangle":
+            sig.append((2, *_v(o.v0), *_v(o.v1), *_v(o.v2), *_v(o.normal),
+                        tuple(o.uv0) if o.uv0 is not None else None, tuple(o.uv1) if o.uv1 is not None else None,
+                        tuple(o.uv2) if o.uv2 is not None else None, ms))
+        else:
+            V, F = o.vertices, o.faces
+            sig.append((3, id(V), V.shape, float(V[:: max(1, V.shape[0] // 1024)].sum()), id(F), F.shape,
+                        int(F[:: max(1, F.shape[0] // 1024)].sum()), None if o.uvs is None else (id(o.uvs), o.uvs.shape), ms))
+    lc, am = getattr(scene, "light_color", None), getattr(scene, "ambient", None)
+    return (tuple(sig), tuple(_v(l) for l in scene.lights), _v(lc) if lc is not None else None, _v(am) if am is not None else None)
+
+
 @dataclass
 class PackedScene:
     semantics: int

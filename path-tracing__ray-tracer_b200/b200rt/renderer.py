@@ -36,7 +36,7 @@ def _torch_real(precision: int):
 def _fingerprint(pixels) -> int:
     import zlib
     a = np.asarray(pixels).reshape(-1)
-    step = max(1, a.size // 65536)
+    step = max(1, a.size // 4096)
     return zlib.crc32(np.ascontiguousarray(a[::step]).tobytes()) ^ (a.size & 0xFFFFFFFF)
 
 
@@ -72,7 +72,7 @@ class _TextureCache:
             if t is not None and getattr(t, "path", None):
                 texs.setdefault(t.path, t)
         paths = texture_paths_sorted(scene)
-        # identity + shape + a strided content fingerprint (<= 64 Ki samples per texture): in-place edits and a freed
+        # identity + shape + a strided content fingerprint (4 Ki samples per texture, ~0.1 ms for the Cornell set): in-place edits and a freed
         # array whose id() is reused by a new array of the same shape are caught without re-reading 52 MB per call
         # (the reference re-reads its textures on every render(), cuda_path_tracer.py:901-932).  invalidate() forces
         # a full re-read after an edit the fingerprint could miss (a single changed texel between two samples).
@@ -133,11 +133,23 @@ class _B200Base(BaseRenderer):
         self.precision = _PREC[precision]
         self.top_nodes = top_nodes
         self._tex_cache = _TextureCache()
+        self._pack_key, self._pack_val = None, None
         self.last_stats: Dict[str, float] = {}
+
+    def _packed(self, scene, host_tex):
+        """``pack_scene`` result, reused while EVERY value the packer reads is unchanged: the key is the tuple of all
+        those floats / ids (reading ~700 attributes costs ~0.15 ms; packing the same scene again 2 ms).  Any edit of any
+        object, material or light — in place or not — changes the key."""
+        from .packer import scene_signature
+        key = (scene_signature(scene), self.semantics, id(host_tex[2]) if host_tex else None,
+               tuple(sorted(host_tex[2].items())) if host_tex else None)
+        if self._pack_key != key:
+            self._pack_val, self._pack_key = pack_scene(scene, self.semantics, textures=host_tex), key
+        return self._pack_val
 
     def _upload(self, scene, camera) -> DeviceScene:
         host_tex, dev_tex = self._tex_cache.get(scene, self.device)
-        packed = pack_scene(scene, self.semantics, textures=host_tex)
+        packed = self._packed(scene, host_tex)
         cam = pack_camera(camera, self.semantics)
         reach = float(np.abs(cam[:3]).max())
         ds = DeviceScene(packed, self.precision, self.device, self.top_nodes, ray_origin_extent=reach,
@@ -157,8 +169,9 @@ class _B200Base(BaseRenderer):
             host = self._host_img = torch.empty(n, dtype=torch.uint8, pin_memory=True)
         host[:n].copy_(u8.reshape(-1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        # frombytes decodes into the image's own storage: exactly one copy out of the reused pinned buffer
-        return Image.frombytes("RGB", (width, height), memoryview(host[:n].numpy()))
+        # one copy out of the reused pinned buffer into an immutable bytes object that the image then references
+        # (frombuffer: no zero-fill of a new image, no second decode copy — 0.5 ms instead of 2 ms at 1080p)
+        return Image.frombuffer("RGB", (width, height), bytes(memoryview(host[:n].numpy())), "raw", "RGB", 0, 1)
 
 
 # ------------------------------------------------------------------------------------------ path tracer
