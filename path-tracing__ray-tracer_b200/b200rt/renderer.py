@@ -50,8 +50,10 @@ class _TextureCache:
     ``enabled=False`` drops level 2, i.e. the textures are re-uploaded from pinned memory on every call (what
     bench.py's end-to-end leg does)."""
 
-    def __init__(self, enabled: bool = True):
+    def __init__(self, enabled: bool = True, sharded: bool = False):
         self.enabled = enabled
+        self.sharded = sharded                  # under torch.distributed: upload 1/N per rank + NVLink all-gather
+        self.uploaded_bytes_rank = 0
         self._key = None
         self._val = None
         self._host = None
@@ -97,18 +99,34 @@ class _TextureCache:
             self._pinned, self._pin_key = pinned, pin_key
             self._n_texels = off
         n = self._n_texels
-        # (2) one H2D copy + RGB8 -> RGBX8 on the device (plumbing, not the hot path)
-        rgb8 = torch.empty(self._pinned.numel(), dtype=torch.uint8, device=device)
-        rgb8.copy_(self._pinned, non_blocking=True)
+        # (2) H2D + RGB8 -> RGBX8 on the device (plumbing, not the hot path).  One process: one copy of the pinned block.
+        # Several ranks on one NVSwitch box hold the SAME host block, so each uploads only its 1/N slice over its own PCIe
+        # link and an in-place NCCL all-gather over NVLink completes every rank's copy: each texture byte crosses PCIe
+        # once per step in total instead of N times through the shared host memory (8 GPUs: 6.5 MB per rank, not 52 MB).
+        total = self._pinned.numel()
+        import torch.distributed as td
+        rank, world = dist.rank_world() if (self.sharded and td.is_available() and td.is_initialized()) else (0, 1)
+        per = (-(-total // world) + 255) & ~255 if world > 1 else total
+        rgb8 = torch.empty(per * world, dtype=torch.uint8, device=device)
+        if world > 1:
+            lo, hi = min(total, rank * per), min(total, (rank + 1) * per)
+            mine = rgb8[rank * per:(rank + 1) * per]
+            if hi > lo:
+                mine[: hi - lo].copy_(self._pinned[lo:hi], non_blocking=True)
+            td.all_gather_into_tensor(rgb8, mine)
+            self.uploaded_bytes_rank = int(hi - lo)
+        else:
+            rgb8[:total].copy_(self._pinned, non_blocking=True)
+            self.uploaded_bytes_rank = int(total)
         texels = torch.empty(max(4, n), dtype=torch.int32, device=device)
         if n:                                             # RGB8 -> RGBX8: one kernel of libb200rt.so (b2rt_expand_rgb8)
             lib = _lib.load()
             _lib.check(lib.b2rt_expand_rgb8(rgb8.data_ptr(), n, texels.data_ptr(), current_stream_ptr(device)),
                        "b2rt_expand_rgb8")
-        info_dev = rgb8[self._info_off:].view(torch.int32)
+        info_dev = rgb8[self._info_off:total].view(torch.int32)
         host = (None, self._info, {p: i for i, p in enumerate(paths)})
         self._key, self._val, self._host = key, (texels, info_dev), host
-        self.uploaded_bytes = int(self._pinned.numel())
+        self.uploaded_bytes = self.uploaded_bytes_rank        # bytes THIS rank moved host -> device
         return host, self._val
 
 
@@ -201,6 +219,7 @@ class B200PathTracer(_B200Base):
         # distributed=False: render every sample on this GPU even inside a torch.distributed job (the N-GPU == 1-GPU
         # image checks compare a split render with this)
         self.distributed = bool(distributed)
+        self._tex_cache.sharded = self.distributed      # collective upload only where every rank renders together
         # progressive=True: successive render() calls with the same size ADD their samples (global sample
         # indices continue where the last call stopped) instead of discarding the previous frame — the
         # accumulation the reference's frame_count reseed hints at (cuda_path_tracer.py:28,739,809)
