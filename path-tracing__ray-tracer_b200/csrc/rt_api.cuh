@@ -1,5 +1,8 @@
 // rt_api.cuh — implementation of the launchers declared in rt_api.h (included by rt_f32.cu / rt_f64.cu).
 #pragma once
+#include <stdlib.h>
+#include <string.h>
+
 #include <type_traits>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -202,6 +205,43 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     if ((e = persistent_grid(count_tests ? (const void *)extend_walk_kernel<R, true> : (const void *)extend_walk_kernel<R, false>, T, smem, &g_walk))) return e;
     if ((e = persistent_grid((const void *)accumulate_kernel<R>, T, 0, &g_simple))) return e;
 
+    // Measured and OFF by default (B2RT_L2_PERSIST=1 turns it on): pinning the hierarchy into the persisting part of the L2
+    // (access-policy window over the node array) while the waves stream gigabytes of queue records past it.  On the
+    // 1 M-triangle scene the step went from 89.3 to 109.2 ms (walk kernel 62.5 -> 75.9 ms): the set-aside takes more from
+    // the triangle records and the queues than it gives the nodes (profiles/r2_c4_l2_persist_ab.log).
+    bool l2_window = false;
+    if (!S.scan_incoherent && S.n_prims > 4096 && S.nodes) {
+        const char *ev = getenv("B2RT_L2_PERSIST");
+        if (ev && atoi(ev) != 0) {
+            int dev = 0, max_persist = 0, max_window = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            const size_t node_bytes = (size_t)(S.n_prims > 1 ? S.n_prims - 1 : 1) * 64;
+            if (max_persist > 0 && max_window > 0) {
+                const size_t win = node_bytes < (size_t)max_window ? node_bytes : (size_t)max_window;
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+                cudaStreamAttrValue av;
+                memset(&av, 0, sizeof av);
+                av.accessPolicyWindow.base_ptr = const_cast<float4 *>(S.nodes);
+                av.accessPolicyWindow.num_bytes = win;
+                av.accessPolicyWindow.hitRatio = (float)((double)max_persist / (double)win < 1.0 ? (double)max_persist / (double)win : 1.0);
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+                if (!l2_window) cudaGetLastError();
+            }
+        }
+    }
+    struct L2Reset {                                            // the stream belongs to the caller: give it back unchanged
+        cudaStream_t st; bool on;
+        ~L2Reset() {
+            if (!on) return;
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);     // later launches: no window
+        }
+    } l2_reset{st, l2_window};
     if (std::is_same<Rng, RefRng>::value) {
         if (!a.pixel_rng) return cudaErrorInvalidValue;
         init_pixel_rng_kernel<<<(npix + 255) / 256, 256, 0, st>>>(W, H, (long long)a.seed, a.sample_offset, a.pixel_rng);
