@@ -72,6 +72,7 @@ class Blob:
         dev = torch.empty(total, dtype=torch.uint8, device=device)
         dev.copy_(host[:total], non_blocking=True)
         _Staging.mark(device)
+        self.host_image = bytes(hv[:total])      # kept so that a cached DeviceScene can re-send its inputs (reupload)
         out = {"_blob": dev}
         for name, arr, off in self.items:
             n = max(arr.nbytes, 16)
@@ -157,7 +158,7 @@ class DeviceScene:
             if self.occluder_hint_host is not None:
                 blob.add("hint", self.occluder_hint_host)
             d = blob.upload(dev)
-            self._blob, self.h2d_small = d["_blob"], blob.nbytes
+            self._blob, self.h2d_small, self._blob_host = d["_blob"], blob.nbytes, blob.host_image
             self.rect, self.sphere, self.tri, self.shade = d["rect"], d["sphere"], d["tri"], d["shade"]
             self.mat, self.lights, self.prim_mat, self.mat_tex = d["mat"], d["lights"], d["prim_mat"], d["mat_tex"]
             if textures_dev is not None:
@@ -216,6 +217,19 @@ class DeviceScene:
             self.occluder_hint = d["hint"]
             s.d_occluder_hint = self.occluder_hint.data_ptr()
         self.struct = s
+
+    def reupload(self, textures_dev=None) -> None:
+        """Send the scene's host image to the device again (one pinned H2D copy into the same buffer) and point the struct
+        at a fresh texture upload.  A renderer that finds the scene unchanged (value signature) keeps this object — its
+        LBVH and derived records are functions of the same bytes — but every ``render()`` still moves its inputs."""
+        n = len(self._blob_host)
+        host = _Staging.get(self.device, n)
+        host.numpy()[:n] = np.frombuffer(self._blob_host, dtype=np.uint8)
+        self._blob.copy_(host[:n], non_blocking=True)
+        _Staging.mark(self.device)
+        if textures_dev is not None:
+            self.texels, self.tex_info = textures_dev
+            self.struct.d_texels, self.struct.d_tex_info = self.texels.data_ptr(), self.tex_info.data_ptr()
 
     def ref(self):
         return C.byref(self.struct)

@@ -487,7 +487,7 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
         if (S.n_lights > 0) {                                               // :265-304
             R nl = R(S.n_lights);
             int li;
-            if constexpr (RNG16) {
+            if (RNG16 && S.n_lights <= 4096) {               // (16 bits resolve up to a few thousand light samples evenly)
                 // one generator step serves the light pick (low 16 bits) and the lobe choice below (high 16 bits)
                 const uint32_t w = PcgRng::word(rng);
                 rng = PcgRng::advance(rng);
@@ -541,7 +541,7 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
         }
         if (go) {
             R choice;                                                       // :317-318
-            if (RNG16 && S.n_lights > 0) choice = R(choice16);
+            if (RNG16 && S.n_lights > 0 && S.n_lights <= 4096) choice = R(choice16);
             else { choice = Rng::template random<R>(rng); rng = Rng::advance(rng); }
             R dn = r.d.x * sf.n.x + r.d.y * sf.n.y + r.d.z * sf.n.z;
             V3<R> refl = {r.d.x - R(2) * dn * sf.n.x, r.d.y - R(2) * dn * sf.n.y, r.d.z - R(2) * dn * sf.n.z};
