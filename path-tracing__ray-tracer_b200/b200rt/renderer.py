@@ -160,8 +160,8 @@ class _B200Base(BaseRenderer):
         those floats / ids (reading ~700 attributes costs ~0.15 ms; packing the same scene again 2 ms).  Any edit of any
         object, material or light — in place or not — changes the key."""
         from .packer import scene_signature
-        key = (scene_signature(scene), self.semantics, id(host_tex[2]) if host_tex else None,
-               tuple(sorted(host_tex[2].items())) if host_tex else None)
+        key = (scene_signature(scene), self.semantics, tuple(sorted(host_tex[2].items())) if host_tex else None,
+               host_tex[1].tobytes() if host_tex and host_tex[1] is not None else None)
         if self._pack_key != key:
             self._pack_val, self._pack_key = pack_scene(scene, self.semantics, textures=host_tex), key
         return self._pack_val
