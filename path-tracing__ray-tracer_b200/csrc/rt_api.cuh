@@ -19,7 +19,7 @@ inline size_t smem_top_bytes(const SceneDev &S) { return (size_t)S.n_top * 64; }
 // Dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel (top levels: up to kTopMax * 64 B,
 // MODE 6 adds the scan and surface records on top).  Returns an error when the request exceeds the device limit.
 inline cudaError_t opt_in_smem(const void *kernel, size_t smem) {
-    if (smem <= 48 * 1024) return cudaSuccess;
+    if (smem <= 40 * 1024) return cudaSuccess;              // (the 48 KB default covers static + dynamic: leave room for the static part)
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
@@ -194,7 +194,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     if ((e = persistent_grid((const void *)shade_kernel<R, Rng, 0>, T, 0, &g_shade))) return e;
     if ((e = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem_bvh, &g_fuse_bvh))) return e;
     // MODE 3 double-buffers its ray records in shared memory (cp.async)
-    const size_t smem_mode3 = smem_scan + ((B2RT_OPT_ASYNC && sizeof(R) == 4) ? 2 * (size_t)kAsyncStageBytes : 0);
+    const size_t smem_mode3 = smem_scan + ((B2RT_OPT_ASYNC && sizeof(R) == 4) ? 2 * (size_t)kAsyncStageBytes + (size_t)kRingBytes : 0);
     if (planar) e = persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_mode3, &g_fuse_scan);
     else e = persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, smem_generic, &g_fuse_scan);
     if (e) return e;

@@ -450,7 +450,7 @@ template <typename R> struct Segment {       // what one loop iteration of cuda_
 
 // One loop iteration of cuda_trace_path (:229-469) for one path: sky / texture / NEE shadow-ray
 // emission / Russian roulette / BSDF sampling.  thr and rng come in through g and are updated.
-template <typename R, typename Rng, bool FIRST, bool GENERIC_HINT, bool SURF>
+template <typename R, typename Rng, bool FIRST, bool GENERIC_HINT, bool SURF, bool HITS_ONLY = false>
 __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueues<R> &Q, const float4 *s_scan,
                                               const float4 *s_surf, const Ray<R> &r, const Hit<R> &h, int slot, int bounce, int max_depth,
                                               Segment<R> &g) {
@@ -463,7 +463,7 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
         R sky = h.prim < 0 ? R(0.1) : R(0);
         Q.L[slot] = Real4<R>::make(sky, sky, sky, R(0));
     }
-    if (h.prim < 0) {                                                       // :234-239 sky
+    if (!HITS_ONLY && h.prim < 0) {                                         // :234-239 sky
 #if B2RT_OPT_SKYQ
         // An escaping path has no shadow ray of its own at this bounce, so its sky term rides in the lane's free
         // shadow-queue slot as a PRE-RESOLVED record (light index -1): the shadow kernel of this bounce adds it to
@@ -590,6 +590,19 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
                                    // read-modify-write of L[slot] in the bounce kernel.  Measured (profiles/r2b): bounce kernels 19.9 ->
                                    // 19.4 ms per 128 spp but the shadow kernels 2.0 -> 4.0 ms: the stall samples on that RMW were hidden
 #endif
+#ifndef B2RT_OPT_RING
+#define B2RT_OPT_RING 0            // 1: the per-warp ring of pending hits below.  MEASURED AND OFF: bounce kernels 34.8 -> 41.4 ms
+                                   // per 256 spp (profiles/r2_hit_ring_ab.log) — the kernel grows from 28.8 to 33.3 KB of SASS (past
+                                   // the 32 KB instruction cache) and spills 116 B at its 64-register budget, which costs more than
+                                   // the full shading lanes win
+#endif
+// Per-warp ring of PENDING HITS (MODE 3).  A quarter of the rays of bounce >= 1 leave the Cornell box through its open
+// front, so shading — 38 % of the instructions — ran with 19 of 32 lanes (profiles/r2_ncu_full_c2.csv).  Each warp now
+// pushes the hits of an iteration into a 64-entry ring in shared memory (structure of arrays: one bank per lane, no
+// conflicts), answers its misses on the spot, and shades only when 32 hits are pending: every shading pass has all
+// lanes on a hit, and every fourth iteration does not shade at all.  Warp-private: __syncwarp, no barrier.
+constexpr int kRingWords = 14;     // P.xyz, d.xyz, thr.xyz, prim, a, b, slot, rng
+constexpr int kRingSlots = 64;
 #ifndef B2RT_OPT_CHUNKED
 #define B2RT_OPT_CHUNKED 1         // 0: one queue-tail atomic per warp iteration (warp_append2) in the small-scene kernels too
 #endif
@@ -600,7 +613,11 @@ __device__ __forceinline__ void shade_segment(const SceneDev &S, const PathQueue
 // grid-stride item global -> shared with cp.async (LDGSTS, no register staging) while it scans and shades the current
 // one; it only ever reads back its own slots, so cp.async.wait_group is all the synchronisation there is.
 // profiles/r2a_*: 15 % of the bounce kernel's stall samples sat on the first use of the just-issued queue loads.
-constexpr int kAsyncStageBytes = 3 * 256 * 16;       // per stage: 3 streams x 256 threads x 16 B
+constexpr int kAsyncStreams = B2RT_OPT_RING ? 2 : 3;  // with the hit ring the throughput record is loaded directly: it is first
+                                                      // needed after the scan, and the ring needs the shared memory
+constexpr int kAsyncStageF4 = kAsyncStreams * 256;    // float4 per stage
+constexpr int kAsyncStageBytes = kAsyncStageF4 * 16;  // per stage: streams x 256 threads x 16 B
+constexpr int kRingBytes = B2RT_OPT_RING ? 8 * kRingWords * kRingSlots * 4 : 0;       // 8 warps per CTA
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -841,27 +858,40 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     if (CHUNKED && (threadIdx.x & 31) == 0) { wc->ray_cur = wc->ray_end = wc->sh_cur = wc->sh_end = 0; }
     if (CHUNKED) __syncwarp();
     int stage = 0;
+    constexpr bool RING = B2RT_OPT_RING && ASYNC;        // MODE 3, float32
+    float *ring = nullptr;
+    __shared__ int s_ring_ctl[8][2];                     // per warp: head, pending hits (lane 0 writes)
+    int *ring_ctl = s_ring_ctl[threadIdx.x >> 5];
+    if constexpr (RING) {
+        ring = reinterpret_cast<float *>(s_ray + 2 * kAsyncStageF4) + (threadIdx.x >> 5) * (kRingWords * kRingSlots);
+        if ((threadIdx.x & 31) == 0) { ring_ctl[0] = 0; ring_ctl[1] = 0; }
+        __syncwarp();
+    }
     if constexpr (ASYNC) {
         const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
         if (i0 < n) {
             cp_async16(s_ray + threadIdx.x, ro + i0);
             cp_async16(s_ray + 256 + threadIdx.x, rd + i0);
-            cp_async16(s_ray + 512 + threadIdx.x, th + i0);
+            if (kAsyncStreams == 3) cp_async16(s_ray + 512 + threadIdx.x, th + i0);
         }
         cp_async_commit();
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        bool valid = i < n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x;; i += gridDim.x * blockDim.x) {
+        const bool more = i < n_round;                   // warp-uniform (n_round is a multiple of 32)
+        if constexpr (RING) { if (!more && ring_ctl[1] == 0) break; }      // one extra pass flushes the last pending hits
+        else { if (!more) break; }
+        bool valid = more && i < n;
         real4<R> qa, qb, qc;
         if constexpr (ASYNC) {
             cp_async_wait_all();
-            const float4 *cur = s_ray + stage * 768 + threadIdx.x;
-            if (valid) { qa = cur[0]; qb = cur[256]; qc = cur[512]; }
+            const float4 *cur = s_ray + stage * kAsyncStageF4 + threadIdx.x;
+            if (valid) { qa = cur[0]; qb = cur[256]; qc = kAsyncStreams == 3 ? cur[512] : ld_stream(th + i); }
             stage ^= 1;
             const int nx = i + gridDim.x * blockDim.x;
-            if (nx < n) {
-                float4 *nxt = s_ray + stage * 768 + threadIdx.x;
-                cp_async16(nxt, ro + nx); cp_async16(nxt + 256, rd + nx); cp_async16(nxt + 512, th + nx);
+            if (more && nx < n) {
+                float4 *nxt = s_ray + stage * kAsyncStageF4 + threadIdx.x;
+                cp_async16(nxt, ro + nx); cp_async16(nxt + 256, rd + nx);
+                if (kAsyncStreams == 3) cp_async16(nxt + 512, th + nx);
             }
             cp_async_commit();
         }
@@ -870,8 +900,10 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         int slot = 0;
         unsigned mask = 0xffffffffu;
         bool dead = false;
+        bool shade_now = false;                          // this lane holds a ray + hit record to shade in this iteration
+        Ray<R> r;
+        Hit<R> h;
         if (valid) {
-            Ray<R> r;
             if (PRIMARY) {                       // cuda_path_trace_kernel's sample set-up (:35-41)
                 const int npix = P.W * P.H;
                 int s, pix, x, y;
@@ -920,7 +952,6 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                 dead = slot < 0;                 // unused remainder of a producer warp's last chunk
             }
             if (!dead) {
-            Hit<R> h;
             if (MODE == 0) {
                 real4<R> hrec = ld_stream(Q.hit + i);
                 h.t = hrec.x; h.prim = (int)(long long)real_as_int(hrec.y); h.a = hrec.z; h.b = hrec.w;
@@ -940,10 +971,45 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                     } else scan_small<false>(S, s_scan, r, 0.001f, 1000000.0f, h);
                 }
             }
-            n_tally += h.prim >= 0 ? 1u : 0u;
-            shade_segment<R, Rng, PRIMARY, (WALK || MODE == 0) && !(sizeof(R) == 4 && MODE == 6), SURF>(S, Q, (PLANAR && !S.occl_hint) ? nullptr : s_scan, s_surf,
-                                                                r, h, slot, bounce, max_depth, g);
+            shade_now = true;
             }
+        }
+        if constexpr (RING) {
+            // misses are answered on the spot (the path ends: sky term into L[slot]); hits go to the ring
+            const bool is_hit = shade_now && h.prim >= 0;
+            if (shade_now && !is_hit) add_sky(Q.L + slot, g.thr.x * R(0.1), g.thr.y * R(0.1), g.thr.z * R(0.1));
+            const unsigned lane = threadIdx.x & 31u, mh = __ballot_sync(0xffffffffu, is_hit);
+            int head = ring_ctl[0], cnt = ring_ctl[1];
+            if (is_hit) {
+                float *e = ring + ((head + cnt + __popc(mh & ((1u << lane) - 1u))) & (kRingSlots - 1));
+                e[0 * kRingSlots] = fmaf(h.t, r.d.x, r.o.x); e[1 * kRingSlots] = fmaf(h.t, r.d.y, r.o.y); e[2 * kRingSlots] = fmaf(h.t, r.d.z, r.o.z);
+                e[3 * kRingSlots] = r.d.x; e[4 * kRingSlots] = r.d.y; e[5 * kRingSlots] = r.d.z;
+                e[6 * kRingSlots] = g.thr.x; e[7 * kRingSlots] = g.thr.y; e[8 * kRingSlots] = g.thr.z;
+                e[9 * kRingSlots] = __int_as_float(h.prim); e[10 * kRingSlots] = h.a; e[11 * kRingSlots] = h.b;
+                e[12 * kRingSlots] = __int_as_float(slot); e[13 * kRingSlots] = __uint_as_float((unsigned)g.rng);
+            }
+            cnt += __popc(mh);
+            __syncwarp();
+            shade_now = false;
+            const int take = (cnt >= 32 || !more) ? min(cnt, 32) : 0;          // full groups; the flush pass takes the rest
+            if ((int)lane < take) {
+                const float *e = ring + ((head + (int)lane) & (kRingSlots - 1));
+                // the hit point stands in for the origin with t = 0: shade_segment computes p = o + t d
+                r.o = {e[0 * kRingSlots], e[1 * kRingSlots], e[2 * kRingSlots]};
+                r.d = {e[3 * kRingSlots], e[4 * kRingSlots], e[5 * kRingSlots]};
+                g.thr = {e[6 * kRingSlots], e[7 * kRingSlots], e[8 * kRingSlots]};
+                h.t = 0.f; h.prim = __float_as_int(e[9 * kRingSlots]); h.a = e[10 * kRingSlots]; h.b = e[11 * kRingSlots];
+                slot = __float_as_int(e[12 * kRingSlots]); g.rng = (uint64_t)__float_as_uint(e[13 * kRingSlots]);
+                shade_now = true;
+            }
+            __syncwarp();
+            if (lane == 0) { ring_ctl[0] = (head + take) & (kRingSlots - 1); ring_ctl[1] = cnt - take; }
+            __syncwarp();
+        }
+        if (shade_now) {
+            n_tally += h.prim >= 0 ? 1u : 0u;
+            shade_segment<R, Rng, PRIMARY, (WALK || MODE == 0) && !(sizeof(R) == 4 && MODE == 6), SURF, RING>(S, Q, (PLANAR && !S.occl_hint) ? nullptr : s_scan, s_surf,
+                                                                r, h, slot, bounce, max_depth, g);
         }
         n_culled += g.culled ? 1u : 0u;
         if (TILED) { t_i += t_step; while (t_i >= n_act) { t_i -= n_act; ++t_s; } }
