@@ -52,6 +52,8 @@ extern "C" {
 
 #define B2RT_PATH_NO_PRIMARY_MASKS 128 /* small scenes: camera rays test every scan record behind one scene-bounds slab test
                                      instead of the per-32-pixel-tile candidate masks (measurement / validation switch) */
+#define B2RT_PATH_NO_SPLIT 256    /* small float32 scenes: bounces >= 1 run the fused scan + shade kernel instead of the split pair
+                                     (closest-hit scan -> hit queue -> shading with every lane on a hit); measurement switch */
 #define B2RT_PATH_COUNT_TESTS 64  /* measurement passes: the persistent walk kernel tallies its box and leaf steps into
                                      d_counters[8] / [9] (a separate kernel instantiation: the timed kernels carry no counters) */
 

@@ -221,11 +221,12 @@ class B200PathTracer(_B200Base):
                  scan_boxes: bool = True, primary_walk: bool = False, surface_records: bool = True,
                  fused_walk: bool = False, walk_primary: bool = False, rects_outside: bool = True,
                  lbvh_rotations: bool = True, distributed: bool = True, count_tests: bool = False,
-                 primary_masks: bool = True):
+                 primary_masks: bool = True, split_bounce: bool = True):
         super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints, scan_boxes,
                          surface_records, rects_outside, lbvh_rotations)
         self.flags = ((0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_walk else 0) | (8 if fused_walk else 0)
-                      | (32 if walk_primary else 0) | (64 if count_tests else 0) | (0 if primary_masks else 128))
+                      | (32 if walk_primary else 0) | (64 if count_tests else 0) | (0 if primary_masks else 128)
+                      | (0 if split_bounce else 256))
         # distributed=False: render every sample on this GPU even inside a torch.distributed job (the N-GPU == 1-GPU
         # image checks compare a split render with this)
         self.distributed = bool(distributed)

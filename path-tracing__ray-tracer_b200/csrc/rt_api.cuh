@@ -118,7 +118,7 @@ template <typename R> struct PathLayout {
         size_t n = (size_t)W * H * spp_per_wave;
         // + the dead remainders of every warp's last chunk (chunked append): <= 148 SMs x 64 resident warps x chunk
         L.stream_bytes = align256((n + (size_t)kQueueSlack) * sizeof(real4<R>));
-        L.counts_off = 11 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance streams
+        L.counts_off = 14 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance + 3 hit-queue streams
         // per-bounce queue tails, unshadowed, culled + one ray-fetch counter per bounce (extend_walk_kernel)
         L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (3 * (size_t)max_depth + 18));
         // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
@@ -156,6 +156,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.ro[0] = stream_at(0); Q.rd[0] = stream_at(1); Q.th[0] = stream_at(2);
     Q.ro[1] = stream_at(3); Q.rd[1] = stream_at(4); Q.th[1] = stream_at(5);
     Q.hit = stream_at(6); Q.so = stream_at(7); Q.sd = stream_at(8); Q.sc = stream_at(9); Q.L = stream_at(10);
+    Q.ha = stream_at(11); Q.hb = stream_at(12); Q.hc = stream_at(13); Q.hd = Q.hit;        // hit queue (split bounce)
     unsigned long long *counts = (unsigned long long *)(base + L.counts_off);
     Q.counts = counts;
     Q.unshadowed = counts + a.max_depth + 1;
@@ -167,6 +168,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     unsigned long long *tile_info = counts + 3 * a.max_depth + 15;          // [2] non-empty tiles, division constants (per call)
     Q.tally = counts + 2 * a.max_depth + 4;                                 // [8] bounds-culled, hits, walk box / leaf steps, sky records
     unsigned long long *fetch = counts + a.max_depth + 3;                   // [max_depth] dynamic-fetch cursors
+    Q.hit_tail = fetch;                                                     // small scenes: hit-queue tails (the walk kernel is unused there)
     const bool sort_rays = S.sort_inv > 0.f && !(a.flags & 2);
     unsigned *keys = (unsigned *)(base + L.sort_off), *keys_sorted = (unsigned *)(base + L.sort_off + L.int_bytes);
     int *iota = (int *)(base + L.sort_off + 2 * L.int_bytes), *perm = (int *)(base + L.sort_off + 3 * L.int_bytes);
@@ -195,6 +197,15 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     if ((e = persistent_grid((const void *)shade_kernel<R, Rng, 1>, T, smem_bvh, &g_fuse_bvh))) return e;
     // MODE 3 double-buffers its ray records in shared memory (cp.async)
     const size_t smem_mode3 = smem_scan + ((B2RT_OPT_ASYNC && sizeof(R) == 4) ? 2 * (size_t)kAsyncStageBytes + (size_t)kRingBytes : 0);
+    // split bounce (small float32 scenes, bounce >= 1): closest-hit scan -> hit queue -> shading with every lane on a hit
+    const bool split = B2RT_OPT_SPLIT && planar && sizeof(R) == 4 && !(a.flags & 256);
+    const size_t smem_scan_k = smem_scan_only + 2 * (size_t)(3 * 256 * 16);
+    const size_t smem_mode7 = smem_scan + 2 * (size_t)kAsyncStageBytes;
+    int g_scan_hits = 0, g_mode7 = 0;
+    if (split) {
+        if ((e = persistent_grid((const void *)scan_hits_kernel<R>, T, smem_scan_k, &g_scan_hits))) return e;
+        if ((e = persistent_grid((const void *)shade_kernel<R, Rng, 7>, T, smem_mode7, &g_mode7))) return e;
+    }
     if (planar) e = persistent_grid((const void *)shade_kernel<R, Rng, 3>, T, smem_mode3, &g_fuse_scan);
     else e = persistent_grid((const void *)shade_kernel<R, Rng, 2>, T, smem_generic, &g_fuse_scan);
     if (e) return e;
@@ -312,6 +323,13 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 prof_end(st);
                 prof_begin(kShade, st);
                 shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);
+                prof_end(st);
+            } else if (fused && scan && split) {
+                prof_begin(kExtend, st);
+                scan_hits_kernel<R><<<g_scan_hits, T, smem_scan_k, st>>>(S, Q, buf, b);
+                prof_end(st);
+                prof_begin(kShade, st);
+                shade_kernel<R, Rng, 7><<<g_mode7, T, smem_mode7, st>>>(S, Q, buf, b, a.max_depth, PA);
                 prof_end(st);
             } else if (fused) {
                 prof_begin(kShade, st);

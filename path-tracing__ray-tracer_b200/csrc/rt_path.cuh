@@ -69,6 +69,10 @@ struct PcgRng {                       // 32-bit PCG-RXS-M-XS stream, seeded by h
 template <typename R> struct PathQueues {
     real4<R> *ro[2], *rd[2], *th[2];      // double-buffered ray queue streams
     real4<R> *hit;                         // (t, prim, a, b)
+    // hit queue of the split small-scene bounce (scan_hits_kernel -> shade_kernel<7>): compacted, hits only
+    //     ha = (hit point.xyz, slot)  hb = (direction.xyz, rng)  hc = (throughput.rgb, prim)  hd = (a, b, -, -)
+    real4<R> *ha, *hb, *hc, *hd;
+    unsigned long long *hit_tail;          // [max_depth] tail of the hit queue of bounce k (low word)
     real4<R> *so, *sd, *sc;                // shadow queue streams
     real4<R> *L;                           // per-path radiance
     // counts[k] = (shadow rays emitted at bounce k-1) << 32 | (rays queued for bounce k): both queue tails move
@@ -812,8 +816,10 @@ template <typename R> struct PrimaryArgs {   // MODE 4: camera-ray generation fu
 template <typename R, typename Rng, int MODE>
 __global__ void __launch_bounds__(256, sizeof(R) != 4 ? 1 : ((MODE == 3 || MODE == 5) ? B2RT_BOUNCE_MIN_BLOCKS : B2RT_BVH_MIN_BLOCKS))
 shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth, PrimaryArgs<R> P) {
+    // MODE 7: consumer of the hit queue (split small-scene bounce): no intersection at all, every item is a hit
+    constexpr bool HITQ = MODE == 7;
     constexpr bool PRIMARY = MODE == 4 || MODE == 5 || MODE == 6, WALK = MODE == 1 || MODE == 4 || MODE == 6,
-                   PLANAR = MODE == 3 || MODE == 5, SURF = B2RT_OPT_SURF && sizeof(R) == 4 && (PLANAR || MODE == 6);
+                   PLANAR = MODE == 3 || MODE == 5, SURF = B2RT_OPT_SURF && sizeof(R) == 4 && (PLANAR || MODE == 6 || HITQ);
     // effective SM clock as the kernels see it: CTA 0's cycle counter against the global nanosecond timer (some GPUs of
     // this pool run sustained FP32 load ~30 % slower at an unchanged nvidia-smi clock reading: bench.py reports both)
     long long clk0 = 0;
@@ -830,14 +836,16 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     // the scan records are what PLANAR modes intersect; MODE 6 and the generic scan (MODE 2) keep them for the
     // occluder hints.  Only these launches pay for the bytes (rt_api.cuh): MODE 0 / 1 / 4 carry generic hints
     // (codes >= 128) and never stage scan records
-    constexpr bool STAGE_SCAN = PLANAR || MODE == 6 || MODE == 2;
-    if (STAGE_SCAN && sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && (PLANAR || S.occl_hint)) {
+    constexpr bool STAGE_SCAN = PLANAR || MODE == 6 || MODE == 2 || HITQ;
+    if (STAGE_SCAN && sizeof(R) == 4 && S.n_scan > 0 && S.scan_incoherent && (PLANAR || HITQ || S.occl_hint)) {
         stage_scan(S, cursor); s_scan = cursor; cursor += 4 * (S.n_scan + S.n_box);
     }
     if (SURF) { stage_surf(S, cursor); s_surf = cursor; cursor += 5 * S.n_prims; }
-    constexpr bool ASYNC = B2RT_OPT_ASYNC && MODE == 3 && sizeof(R) == 4;
+    constexpr bool ASYNC = B2RT_OPT_ASYNC && (MODE == 3 || HITQ) && sizeof(R) == 4;
     float4 *s_ray = cursor;                                                  // [2 stages][3 streams][256 threads]
-    const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
+    // the hit queue has the ray queue's first three record layouts (hit point for origin, primitive for depth)
+    const real4<R> *__restrict__ ro = HITQ ? Q.ha : Q.ro[in_buf], *__restrict__ rd = HITQ ? Q.hb : Q.rd[in_buf],
+                   *__restrict__ th = HITQ ? Q.hc : Q.th[in_buf];
     real4<R> *__restrict__ no = Q.ro[in_buf ^ 1], *__restrict__ nd = Q.rd[in_buf ^ 1], *__restrict__ nt = Q.th[in_buf ^ 1];
     // tile-list mode (MODE 5 with candidate masks): item i = ((sample * non-empty tiles + tile index) * 32 + lane)
     const bool TILED = PLANAR && PRIMARY && B2RT_OPT_MASKS && B2RT_OPT_TILE_LIST && P.masks != nullptr;
@@ -846,7 +854,8 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
     unsigned t_s = 0, t_i = 0;
     const unsigned t_step = (gridDim.x * blockDim.x) >> 5;
     if (TILED) { const unsigned g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t_s = g0 / n_act; t_i = g0 - t_s * n_act; }
-    int n = PRIMARY ? (TILED ? (int)n_act * 32 * P.spp_wave : P.W * P.H * P.spp_wave) : ray_count(Q, bounce);
+    int n = PRIMARY ? (TILED ? (int)n_act * 32 * P.spp_wave : P.W * P.H * P.spp_wave)
+                    : (HITQ ? (int)(Q.hit_tail[bounce] & 0xffffffffULL) : ray_count(Q, bounce));
     // ray statistics: every camera ray counts as answered, whether its tile was visited or not
     if (PRIMARY && blockIdx.x == 0 && threadIdx.x == 0) Q.counts[0] = (unsigned long long)(P.W * P.H * P.spp_wave);
     int n_round = (n + 31) & ~31;                // whole warps iterate together (ballots in warp_append2)
@@ -901,6 +910,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         unsigned mask = 0xffffffffu;
         bool dead = false;
         bool shade_now = false;                          // this lane holds a ray + hit record to shade in this iteration
+        int hitq_prim = -1;
         Ray<R> r;
         Hit<R> h;
         if (valid) {
@@ -948,11 +958,16 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
                 slot = (int)unpack_u<R>(a.w);
                 g.rng = unpack_u<R>(b.w);
                 g.thr = xyz<R>(c);
+                if (HITQ) hitq_prim = (int)unpack_u<R>(c.w);
                 prefetch_l2(Q.L + slot);         // a miss adds the sky term to L[slot]: DRAM round trip started now
                 dead = slot < 0;                 // unused remainder of a producer warp's last chunk
             }
             if (!dead) {
-            if (MODE == 0) {
+            if (HITQ) {
+                // (the record's .w lane of the third stream was unpacked as "depth" into nothing: it is the primitive)
+                const real4<R> ab = ld_stream(Q.hd + i);
+                h.t = R(0); h.prim = hitq_prim; h.a = ab.x; h.b = ab.y;       // p = o + 0 d: the stored hit point
+            } else if (MODE == 0) {
                 real4<R> hrec = ld_stream(Q.hit + i);
                 h.t = hrec.x; h.prim = (int)(long long)real_as_int(hrec.y); h.a = hrec.z; h.b = hrec.w;
             } else if (WALK) {
@@ -1008,7 +1023,7 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         }
         if (shade_now) {
             n_tally += h.prim >= 0 ? 1u : 0u;
-            shade_segment<R, Rng, PRIMARY, (WALK || MODE == 0) && !(sizeof(R) == 4 && MODE == 6), SURF, RING>(S, Q, (PLANAR && !S.occl_hint) ? nullptr : s_scan, s_surf,
+            shade_segment<R, Rng, PRIMARY, (WALK || MODE == 0) && !(sizeof(R) == 4 && MODE == 6), SURF, RING || HITQ>(S, Q, ((PLANAR || HITQ) && !S.occl_hint) ? nullptr : s_scan, s_surf,
                                                                 r, h, slot, bounce, max_depth, g);
         }
         n_culled += g.culled ? 1u : 0u;
@@ -1059,6 +1074,90 @@ shade_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce, int max_depth,
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
         atomicAdd(Q.clk, (unsigned long long)(clock64() - clk0));
         atomicAdd(Q.clk + 1, ns1 - ns0);
+    }
+}
+
+// ------------------------------------------------------------------------------------ split bounce: closest hit only
+// Small float32 scenes, bounce >= 1 (B2RT_OPT_SPLIT).  The fused bounce kernel shades with 19 of 32 lanes because a
+// quarter of these rays leave the box, and at 29 KB of SASS / 64 registers it has neither instruction cache nor
+// registers to spare for a fix inside (the per-warp hit ring was measured: slower).  Split in two instead:
+//   scan_hits_kernel   ray queue -> record scan; a miss ends the path here (sky term into L[slot]); a hit is appended
+//                      to the HIT QUEUE (hit point, direction, throughput, primitive, rng: 64 B), chunked like every queue
+//   shade_kernel<7>    hit queue -> shading, every lane on a hit -> next ray queue + shadow queue
+// Both kernels are small (the scan has no shading state, the shade no scan), so they fit the instruction cache with room
+// and hold more warps.  Costs 64 B written + read per hit; the wavefront is nowhere near HBM-bound.
+// MEASURED AND OFF (profiles/r2_split_bounce_ab.log, r2_ncu_split_bounce.csv): bounces >= 1 take 31.5 instead of 27.2 ms per
+// 256 spp.  Bounce 1 under ncu: scan 0.73 ms + shade 0.62 ms against 1.17 ms fused; the pair moves 7.1 GB of DRAM traffic
+// where the fused kernel moves 4.0 GB and both halves sit at 62-66 % of the DRAM peak with long-scoreboard 4.9 / 7.0 per
+// issue — the instructions saved (shading at 26 instead of 19 lanes) are paid for in bandwidth.  Fusion stays.
+#ifndef B2RT_OPT_SPLIT
+#define B2RT_OPT_SPLIT 0
+#endif
+#ifndef B2RT_SCAN_MIN_BLOCKS
+#define B2RT_SCAN_MIN_BLOCKS 5          // measured 4 / 5 / 6: 17.0 / 17.1 / 18.4 ms per 256 spp
+#endif
+template <typename R>
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? B2RT_SCAN_MIN_BLOCKS : 1)
+scan_hits_kernel(SceneDev S, PathQueues<R> Q, int in_buf, int bounce) {
+    extern __shared__ float4 s_dyn[];
+    float4 *s_scan = s_dyn;
+    stage_scan(S, s_scan);
+    float4 *s_ray = s_scan + 4 * (S.n_scan + S.n_box);                       // [2 stages][3 streams][256 threads]
+    const real4<R> *__restrict__ ro = Q.ro[in_buf], *__restrict__ rd = Q.rd[in_buf], *__restrict__ th = Q.th[in_buf];
+    const int n = ray_count(Q, bounce), n_round = (n + 31) & ~31;
+    __shared__ WarpCursor s_wc[8];
+    WarpCursor *wc = s_wc + (threadIdx.x >> 5);
+    if ((threadIdx.x & 31) == 0) { wc->ray_cur = wc->ray_end = wc->sh_cur = wc->sh_end = 0; }
+    __syncwarp();
+    unsigned *tail = reinterpret_cast<unsigned *>(Q.hit_tail + bounce);
+    int stage = 0;
+    if constexpr (sizeof(R) == 4) {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i0 < n) { cp_async16(s_ray + threadIdx.x, ro + i0); cp_async16(s_ray + 256 + threadIdx.x, rd + i0); cp_async16(s_ray + 512 + threadIdx.x, th + i0); }
+        cp_async_commit();
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        bool is_hit = false;
+        Ray<R> r; Hit<R> h; real4<R> a, b, c;
+        if constexpr (sizeof(R) == 4) {
+            cp_async_wait_all();
+            const float4 *cur = s_ray + stage * 768 + threadIdx.x;
+            if (valid) { a = cur[0]; b = cur[256]; c = cur[512]; }
+            stage ^= 1;
+            const int nx = i + gridDim.x * blockDim.x;
+            if (nx < n) { float4 *nxt = s_ray + stage * 768 + threadIdx.x; cp_async16(nxt, ro + nx); cp_async16(nxt + 256, rd + nx); cp_async16(nxt + 512, th + nx); }
+            cp_async_commit();
+        } else if (valid) { a = ld_stream(ro + i); b = ld_stream(rd + i); c = ld_stream(th + i); }
+        int slot = -1;
+        if (valid) {
+            slot = (int)unpack_u<R>(a.w);
+            if (slot >= 0) {                                                 // not a dead chunk remainder
+                r.o = xyz<R>(a); r.d = xyz<R>(b);
+                if constexpr (sizeof(R) == 4) scan_small<false>(S, s_scan, r, 0.001f, 1000000.0f, h);
+                else { h.prim = -1; h.t = R(0); h.a = h.b = R(0); }
+                is_hit = h.prim >= 0;
+                if (!is_hit) add_sky(Q.L + slot, c.x * R(0.1), c.y * R(0.1), c.z * R(0.1));      // :234-239: the path ends here
+            }
+        }
+        const unsigned mh = __ballot_sync(0xffffffffu, is_hit);
+        if (mh) {
+            int cur_ = wc->ray_cur, end_ = wc->ray_end;
+            const int k = chunk_take(tail, cur_, end_, mh, threadIdx.x & 31u);
+            if ((threadIdx.x & 31) == 0) { wc->ray_cur = cur_; wc->ray_end = end_; }
+            __syncwarp();
+            if (is_hit) {
+                st_stream(Q.ha + k, Real4<R>::make(r.o.x + r.d.x * h.t, r.o.y + r.d.y * h.t, r.o.z + r.d.z * h.t, a.w));
+                st_stream(Q.hb + k, b);
+                st_stream(Q.hc + k, Real4<R>::make(c.x, c.y, c.z, pack_int<R>((int64_t)h.prim)));
+                st_stream(Q.hd + k, Real4<R>::make(h.a, h.b, R(0), R(0)));
+            }
+        }
+    }
+    {   // dead remainder of this warp's last chunk
+        const int lane = threadIdx.x & 31, rc = wc->ray_cur, re = wc->ray_end;
+#pragma unroll 1
+        for (int k = rc + lane; k < re; k += 32) st_stream(Q.ha + k, Real4<R>::make(R(0), R(0), R(0), pack_int<R>(-1)));
     }
 }
 
