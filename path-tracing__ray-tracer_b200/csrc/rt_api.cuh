@@ -118,7 +118,8 @@ template <typename R> struct PathLayout {
         size_t n = (size_t)W * H * spp_per_wave;
         // + the dead remainders of every warp's last chunk (chunked append): <= 148 SMs x 64 resident warps x chunk
         L.stream_bytes = align256((n + (size_t)kQueueSlack) * sizeof(real4<R>));
-        L.counts_off = 14 * L.stream_bytes;              // 6 ray + 1 hit + 3 shadow + 1 radiance + 3 hit-queue streams
+        // 6 ray + 1 hit + 3 shadow + 1 radiance streams (+ 3 hit-queue streams in a B2RT_OPT_SPLIT build)
+        L.counts_off = (B2RT_OPT_SPLIT ? 14 : 11) * L.stream_bytes;
         // per-bounce queue tails, unshadowed, culled + one ray-fetch counter per bounce (extend_walk_kernel)
         L.sort_off = L.counts_off + align256(sizeof(unsigned long long) * (3 * (size_t)max_depth + 18));
         // ray re-ordering (LBVH scenes): keys, sorted keys, iota, permutation + CUB scratch
@@ -156,7 +157,8 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     Q.ro[0] = stream_at(0); Q.rd[0] = stream_at(1); Q.th[0] = stream_at(2);
     Q.ro[1] = stream_at(3); Q.rd[1] = stream_at(4); Q.th[1] = stream_at(5);
     Q.hit = stream_at(6); Q.so = stream_at(7); Q.sd = stream_at(8); Q.sc = stream_at(9); Q.L = stream_at(10);
-    Q.ha = stream_at(11); Q.hb = stream_at(12); Q.hc = stream_at(13); Q.hd = Q.hit;        // hit queue (split bounce)
+    Q.ha = Q.hb = Q.hc = Q.hd = nullptr;
+    if (B2RT_OPT_SPLIT) { Q.ha = stream_at(11); Q.hb = stream_at(12); Q.hc = stream_at(13); Q.hd = Q.hit; }      // hit queue (split bounce)
     unsigned long long *counts = (unsigned long long *)(base + L.counts_off);
     Q.counts = counts;
     Q.unshadowed = counts + a.max_depth + 1;
