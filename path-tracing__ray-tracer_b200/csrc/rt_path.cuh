@@ -130,7 +130,10 @@ template <typename R> __device__ __forceinline__ int shadow_count(const PathQueu
 // to the tail only when the chunk is used up (one atomic per ~5 iterations); an append that does not fit fills the old
 // chunk and continues in the new one, so the only unused slots are each warp's last chunk remainder, which the warp
 // marks dead (slot word -1) before it exits — consumers skip those, the statistics subtract them (Q.dead).
-constexpr int kQueueChunk = 128;
+#ifndef B2RT_QCHUNK
+#define B2RT_QCHUNK 128
+#endif
+constexpr int kQueueChunk = B2RT_QCHUNK;
 struct WarpCursor { int ray_cur, ray_end, sh_cur, sh_end; };     // shared memory, one per warp, written by lane 0
 
 // refill path, out of line (the bounce kernels live next to the instruction-cache limit): takes a new chunk from the tail
