@@ -243,6 +243,7 @@ class B200PathTracer(_B200Base):
         self.frame_count = 0                    # like CUDAPathTracer.frame_count (:739,:809)
         self._ws = None
         self._symm, self._symm_key = None, None
+        self._auto_wp = {}
 
     def get_capabilities(self) -> List[str]:
         return ["path_tracing", "global_illumination", "monte_carlo_integration", "color_bleeding", "shadows",
@@ -310,6 +311,8 @@ class B200PathTracer(_B200Base):
         2^26 (their queues are also sorted).  The spp are spread evenly over the waves."""
         wp = self.wave_paths
         if wp is None:
+            wp = self._auto_wp.get(small_scene)          # cudaMemGetInfo costs ~20 ms next to a 50 GB allocation: ask once
+        if wp is None:
             wp = (1 << 28) if small_scene else (1 << 26)
             try:
                 free, _ = torch.cuda.mem_get_info(self.device)
@@ -319,6 +322,7 @@ class B200PathTracer(_B200Base):
                     wp >>= 1
             except Exception:
                 wp = 1 << 26
+            self._auto_wp[small_scene] = wp
         per_wave = max(1, wp // max(1, npix))
         spp_local = max(1, spp_local)
         n_waves = -(-spp_local // per_wave)
