@@ -307,6 +307,9 @@ def extra_c4(dev, steps: int = 2):
                                        ds.sphere.data_ptr(), ds.tri.data_ptr(), C.c_float(ds.box_pad),
                                        ds.nodes.data_ptr(), ds.top.data_ptr(), ds.n_top, meta, temp.data_ptr(),
                                        temp.numel(), current_stream_ptr(dev), 1 if ds.rects_outside else 0), "lbvh")
+        if ds.wide is not None:                                         # the 4-wide nodes are part of the build
+            _lib.check(lib.b2rt_lbvh_widen(ds.nodes.data_ptr(), ds.top.data_ptr(), meta[0], meta[2], ds.wide.data_ptr(),
+                                           ds.wide.numel(), current_stream_ptr(dev)), "widen")
         e1.record(); torch.cuda.synchronize(dev)
         times.append(e0.elapsed_time(e1))
     build_ms = float(np.median(times[1:]))
@@ -334,6 +337,8 @@ def extra_c4(dev, steps: int = 2):
     nodes_per_ray, leaves_per_ray = cc[8] / walk_rays, cc[9] / walk_rays
     walk_ms = ms[1] / steps
     walk_rays_step = (c[1] - c[0]) / steps
+    wide = ds.wide is not None                                          # 4-wide nodes: 128 B and four slab tests per box step
+    node_bytes, node_slabs = (128.0, 4) if wide else (64.0, 2)
     out = {
         "workload": "heightfield_1M_triangles_1920x1080_64spp_depth4", "dtype": "f32", "n_prims": int(n),
         "lbvh_build_ms": build_ms, "lbvh_mtris_per_s": n / build_ms / 1e3,
@@ -341,9 +346,10 @@ def extra_c4(dev, steps: int = 2):
         "kernel_ms_per_step": {k: ms[i] / steps for i, k in enumerate(["raygen", "walk", "bounce0_and_shade", "shadow", "accumulate", "ray_sort"])},
         "walk_kernel": {"ms_per_step": walk_ms, "grays_per_s": walk_rays_step / (walk_ms * 1e-3) / 1e9 if walk_ms else None,
                         "box_steps_per_ray": nodes_per_ray, "leaf_steps_per_ray": leaves_per_ray,
-                        "algorithmic_bytes_per_ray": nodes_per_ray * 64.0 + leaves_per_ray * 48.0 + 48.0 + 16.0,
-                        "executed_tflops": walk_rays_step * (nodes_per_ray * 2 * COST["slab"] + leaves_per_ray * COST["triangle"]) / (walk_ms * 1e-3) / 1e12 if walk_ms else None,
-                        "note": "box step = one 64 B node (two child boxes), leaf step = one 48 B triangle; + 48 B ray in, 16 B hit out"},
+                        "node_width": node_slabs,
+                        "algorithmic_bytes_per_ray": nodes_per_ray * node_bytes + leaves_per_ray * 48.0 + 48.0 + 16.0,
+                        "executed_tflops": walk_rays_step * (nodes_per_ray * node_slabs * COST["slab"] + leaves_per_ray * COST["triangle"]) / (walk_ms * 1e-3) / 1e12 if walk_ms else None,
+                        "note": "box step = one %d B node (%d child boxes), leaf step = one 48 B triangle; + 48 B ray in, 16 B hit out" % (int(node_bytes), node_slabs)},
         "host_scene_build_s": host_s, "prepare_s_incl_pack_upload_lbvh": prepare_s,
     }
     del r, rc, st, stc

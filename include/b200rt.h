@@ -54,6 +54,8 @@ extern "C" {
                                      instead of the per-32-pixel-tile candidate masks (measurement / validation switch) */
 #define B2RT_PATH_NO_SPLIT 256    /* small float32 scenes: bounces >= 1 run the fused scan + shade kernel instead of the split pair
                                      (closest-hit scan -> hit queue -> shading with every lane on a hit); measurement switch */
+#define B2RT_PATH_BINARY_WALK 512  /* large scenes: the persistent walk kernel reads the two-wide nodes even when the scene
+                                     carries d_bvh_wide (measurement / validation switch: results are identical) */
 #define B2RT_PATH_COUNT_TESTS 64  /* measurement passes: the persistent walk kernel tallies its box and leaf steps into
                                      d_counters[8] / [9] (a separate kernel instantiation: the timed kernels carry no counters) */
 
@@ -76,7 +78,7 @@ extern "C" {
  * replaces the AoS float32 block of _prepare_scene_data / _prepare_light_data
  * (cuda_path_tracer.py:819-899,942-946).
  */
-#define B2RT_ABI_VERSION 2       /* layout of b2rt_scene below; bumped whenever a field is added, moved or re-interpreted */
+#define B2RT_ABI_VERSION 3       /* layout of b2rt_scene below; bumped whenever a field is added, moved or re-interpreted */
 #define B2RT_SCAN_MAX_PRIMS 64   /* scenes up to this size scan all primitives for incoherent rays (scan_incoherent) */
 
 typedef struct b2rt_scene {
@@ -144,6 +146,10 @@ typedef struct b2rt_scene {
     /* Outward-padded bounds of all primitives (lo > hi: unknown).  Camera rays of small scenes are tested against
      * them first: on the Cornell box 51 % of the primary rays miss the scene and skip the record scan. */
     float bounds_lo[3], bounds_hi[3];
+    /* Optional (ABI 3; NULL: the two-wide nodes are walked): 4-wide nodes written by b2rt_lbvh_widen, float4[8 * (n_bvh_top +
+     * n_internal)].  The persistent walk kernel that traces the incoherent rays (bounce >= 1) of float32 scenes too large
+     * for the record scan reads these instead of d_bvh_nodes: half the dependent fetches per ray. */
+    const void *d_bvh_wide;
 } b2rt_scene;
 
 const char *b2rt_last_error(void);
@@ -196,6 +202,14 @@ int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri,
                     const void *d_rect_f32, const void *d_sphere_f32, const void *d_tri_f32,
                     float box_pad, void *d_nodes_out, void *d_top_out, int32_t top_capacity,
                     int32_t *h_meta_out, void *d_temp, size_t temp_bytes, void *stream, int32_t flags);
+/* 4-wide nodes from a finished hierarchy (d_nodes / d_top / n_top / n_internal exactly as b2rt_lbvh_build left them):
+ * entry `ref` (a child reference: < n_top top copy, else n_top + node index) holds the boxes and references of that
+ * node's GRANDCHILDREN — 8 float4 = one 128 B line: lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] bits(ref[4]) unused;
+ * a leaf child stays one slot, an empty slot has ref 0x80000000.  Asynchronous on the stream.  (The reference has no
+ * counterpart: its BVHNode is a binary tree of Python objects, core/acceleration.py:8-30.) */
+int b2rt_lbvh_wide_bytes(int32_t n_top, int32_t n_internal, size_t *h_bytes);
+int b2rt_lbvh_widen(const void *d_nodes, const void *d_top, int32_t n_top, int32_t n_internal, void *d_wide_out,
+                    size_t wide_bytes, void *stream);
 /* flags for b2rt_lbvh_build */
 #define B2RT_LBVH_NO_ROTATIONS 2  /* skip the bottom-up tree-rotation pass (measurement switch) */
 #define B2RT_LBVH_RECTS_OUTSIDE 1 /* the rectangles get no place in the hierarchy (set b2rt_scene.bvh_rects_outside too: every

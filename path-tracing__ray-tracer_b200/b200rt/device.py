@@ -100,7 +100,7 @@ class DeviceScene:
                  top_nodes: int = TOP_NODES_DEFAULT, ray_origin_extent: float = 0.0, textures_dev=None,
                  scan_max_prims: int = SCAN_MAX_PRIMS, occluder_hints: bool = True, ray_sort_min_prims: int = 4096,
                  scan_boxes: bool = True, surface_records: bool = True, rects_outside: bool = True,
-                 lbvh_rotations: bool = True, prepare: str = "library"):
+                 lbvh_rotations: bool = True, prepare: str = "library", wide_nodes: bool = False):
         """``prepare``: who derives the small-scene records (scan / box / surface records, occluder hints, bounds) —
         ``"library"`` = ``b2rt_scene_prepare_host`` inside ``libb200rt.so`` (what any C-ABI binder gets), ``"numpy"`` =
         the independent implementation in ``packer.py`` (kept as the cross-check; the CPU tests compare the two)."""
@@ -190,6 +190,19 @@ class DeviceScene:
                                                 (1 if self.rects_outside else 0) | (0 if lbvh_rotations else 2)),
                        "b2rt_lbvh_build")
             self.n_top, self.root, self.n_internal = int(meta[0]), int(meta[1]), int(meta[2])
+            # wide_nodes (off by default): 4-wide nodes for the persistent walk kernel of float32 scenes too large for the
+            # record scan, derived on the device from the finished tree (128 B per node reference).  Measured on the
+            # 1 M-triangle scene: 14.4 instead of 28.8 box steps per ray, identical hits, but 65.0 vs 62.4 ms per step in
+            # the walk kernel — its stalls are the DRAM misses of the bottom levels, which a wider node does not remove
+            # (profiles/r2_c4_wide_nodes_ab.log)
+            self.wide = None
+            if wide_nodes and precision == _lib.P_F32 and not scan_ok and self.n_internal > 0:
+                wb = C.c_size_t(0)
+                _lib.check(self.lib.b2rt_lbvh_wide_bytes(self.n_top, self.n_internal, C.byref(wb)), "b2rt_lbvh_wide_bytes")
+                self.wide = torch.empty(wb.value, dtype=torch.uint8, device=dev)
+                _lib.check(self.lib.b2rt_lbvh_widen(self.nodes.data_ptr(), self.top.data_ptr(), self.n_top, self.n_internal,
+                                                    self.wide.data_ptr(), wb.value, current_stream_ptr(dev)),
+                           "b2rt_lbvh_widen")
         s = _lib.new_scene_struct()
         s.precision, s.semantics = precision, packed.semantics
         s.n_rect, s.n_sphere, s.n_tri = packed.n_rect, packed.n_sphere, packed.n_tri
@@ -198,6 +211,7 @@ class DeviceScene:
         s.d_prim_mat, s.d_mat, s.d_mat_tex = self.prim_mat.data_ptr(), self.mat.data_ptr(), self.mat_tex.data_ptr()
         s.d_texels, s.d_tex_info, s.d_lights = self.texels.data_ptr(), self.tex_info.data_ptr(), self.lights.data_ptr()
         s.d_bvh_nodes, s.d_bvh_top = self.nodes.data_ptr(), self.top.data_ptr()
+        s.d_bvh_wide = self.wide.data_ptr() if self.wide is not None else None
         s.n_bvh_top, s.bvh_root = self.n_top, self.root
         s.scan_incoherent = 1 if scan_ok else 0
         s.bvh_rects_outside = 1 if self.rects_outside else 0

@@ -159,6 +159,19 @@ int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri, const void 
     return 0;
 }
 
+int b2rt_lbvh_wide_bytes(int32_t n_top, int32_t n_internal, size_t *h_bytes) {
+    *h_bytes = b2rt::lbvh_wide_bytes(n_top, n_internal);
+    return 0;
+}
+
+int b2rt_lbvh_widen(const void *d_nodes, const void *d_top, int32_t n_top, int32_t n_internal, void *d_wide_out,
+                    size_t wide_bytes, void *stream) {
+    cudaError_t e = b2rt::lbvh_widen((const float4 *)d_nodes, (const float4 *)d_top, n_top, n_internal, (float4 *)d_wide_out,
+                                     wide_bytes, S(stream));
+    if (e) return fail("b2rt_lbvh_widen", e);
+    return 0;
+}
+
 static int check_scene(const b2rt_scene *s) {
     if (!s) return fail_msg("scene is NULL");
     if (s->struct_size != sizeof(b2rt_scene) || s->abi_version != B2RT_ABI_VERSION) {

@@ -414,6 +414,51 @@ __global__ void finalize_kernel(int n_internal, const int *top_id, int *meta, fl
     }
 }
 
+// 4-wide nodes for the persistent walk kernel of large scenes (rt_path.cuh:extend_walk_kernel<.., WIDE>).
+// That kernel is bound by the latency of its dependent node fetches (one 64 B node per box step, 28.8 steps per ray on
+// the 1 M-triangle scene), so the remedy is fewer, fatter steps: wide[ref] holds the boxes and references of the
+// GRANDCHILDREN of binary node `ref` (a leaf child stays one slot), one 128 B line, and a walk that starts at the root
+// only ever lands on every other level of the binary tree.  Every reference gets a wide node — half of them are never
+// visited, which costs build bandwidth (< 0.1 ms per million) but no cache footprint, and needs no depth pass.
+// References keep the final encoding of finalize_kernel (< n_top: top copy, >= n_top: n_top + node index, < 0: ~prim),
+// so wide[] is indexed by the reference itself.  Layout (8 float4):
+//   lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] bits(ref[4]) -      empty slot: ref = 0x80000000
+__global__ void widen_kernel(int n_refs, int n_top, const float4 *__restrict__ nodes, const float4 *__restrict__ top,
+                             float4 *__restrict__ wide) {
+    const int ref = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ref >= n_refs) return;
+    auto record = [&](int r) { return r < n_top ? top + 4 * (size_t)r : nodes + 4 * (size_t)(r - n_top); };
+    float lo[3][4], hi[3][4];
+    int c[4];
+    for (int k = 0; k < 4; ++k) {
+        c[k] = (int)0x80000000;
+        for (int a = 0; a < 3; ++a) lo[a][k] = hi[a][k] = 0.f;
+    }
+    int k = 0;
+    auto put = [&](float x0, float y0, float z0, float x1, float y1, float z1, int r) {
+        lo[0][k] = x0; lo[1][k] = y0; lo[2][k] = z0; hi[0][k] = x1; hi[1][k] = y1; hi[2][k] = z1; c[k] = r;
+        ++k;
+    };
+    auto expand = [&](float x0, float y0, float z0, float x1, float y1, float z1, int r) {
+        if (r < 0) { put(x0, y0, z0, x1, y1, z1, r); return; }           // a leaf child is one slot
+        const float4 *q = record(r);
+        const float4 m0 = q[0], m1 = q[1], m2 = q[2], m3 = q[3];
+        put(m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, __float_as_int(m3.x));
+        put(m1.z, m1.w, m2.x, m2.y, m2.z, m2.w, __float_as_int(m3.y));
+    };
+    const float4 *p = record(ref);
+    const float4 n0 = p[0], n1 = p[1], n2 = p[2], n3 = p[3];
+    expand(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, __float_as_int(n3.x));
+    expand(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, __float_as_int(n3.y));
+    float4 *w = wide + 8 * (size_t)ref;
+    for (int a = 0; a < 3; ++a) {
+        w[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+        w[3 + a] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+    }
+    w[6] = make_float4(__int_as_float(c[0]), __int_as_float(c[1]), __int_as_float(c[2]), __int_as_float(c[3]));
+    w[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct TempLayout {
@@ -513,6 +558,21 @@ cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, 
     if ((e = cudaStreamSynchronize(stream))) return e;
     h_meta[0] = hm[0]; h_meta[1] = hm[1]; h_meta[2] = hm[2];
     return cudaSuccess;
+}
+
+size_t lbvh_wide_bytes(int n_top, int n_internal) {
+    const size_t n = (size_t)(n_top > 0 ? n_top : 0) + (size_t)(n_internal > 0 ? n_internal : 0);
+    return (n > 0 ? n : 1) * 128;
+}
+
+cudaError_t lbvh_widen(const float4 *nodes, const float4 *top, int n_top, int n_internal, float4 *wide, size_t wide_bytes,
+                       cudaStream_t stream) {
+    if (n_top < 0 || n_internal < 0 || (n_internal > 0 && (!nodes || !wide)) || (n_top > 0 && !top)) return cudaErrorInvalidValue;
+    if (wide_bytes < lbvh_wide_bytes(n_top, n_internal)) return cudaErrorInvalidValue;
+    const int n_refs = n_top + n_internal;
+    if (n_internal == 0) return cudaSuccess;                  // no internal node: the root reference is a leaf (or nothing)
+    widen_kernel<<<(n_refs + 255) / 256, 256, 0, stream>>>(n_refs, n_top, nodes, top, wide);
+    return cudaGetLastError();
 }
 
 }  // namespace b2rt

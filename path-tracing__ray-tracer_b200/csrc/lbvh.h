@@ -9,4 +9,8 @@ size_t lbvh_temp_bytes(int n_prims);
 cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, const float4 *sphere, const float4 *tri,
                        float pad, float4 *nodes, float4 *top, int top_capacity, int *h_meta, void *temp,
                        size_t temp_bytes, cudaStream_t stream, int build_flags = 0);
+// 4-wide nodes (128 B each, indexed by the child reference) derived from a finished hierarchy; see lbvh.cu:widen_kernel
+size_t lbvh_wide_bytes(int n_top, int n_internal);
+cudaError_t lbvh_widen(const float4 *nodes, const float4 *top, int n_top, int n_internal, float4 *wide, size_t wide_bytes,
+                       cudaStream_t stream);
 }  // namespace b2rt

@@ -215,7 +215,14 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     // large scenes: incoherent bounces run the persistent walk kernel + the wavefront shade stage
     const bool walk_kernel = fused && sizeof(R) == 4 && !S.scan_incoherent && !(a.flags & 8);
     const bool count_tests = (a.flags & 64) != 0;
-    if ((e = persistent_grid(count_tests ? (const void *)extend_walk_kernel<R, true> : (const void *)extend_walk_kernel<R, false>, T, smem, &g_walk))) return e;
+    // float32 scenes that carry 4-wide nodes (b2rt_lbvh_widen) walk those: half the dependent node fetches per ray
+    const bool wide_walk = walk_kernel && S.wide != nullptr && !(a.flags & 512);
+    const size_t smem_walk = wide_walk ? 0 : smem;
+    const void *k_walk = count_tests ? (const void *)extend_walk_kernel<R, true, false> : (const void *)extend_walk_kernel<R, false, false>;
+    if constexpr (sizeof(R) == 4) {
+        if (wide_walk) k_walk = count_tests ? (const void *)extend_walk_kernel<R, true, true> : (const void *)extend_walk_kernel<R, false, true>;
+    }
+    if ((e = persistent_grid(k_walk, T, smem_walk, &g_walk))) return e;
     if ((e = persistent_grid((const void *)accumulate_kernel<R>, T, 0, &g_simple))) return e;
 
     // Measured and OFF by default (B2RT_L2_PERSIST=1 turns it on): pinning the hierarchy into the persisting part of the L2
@@ -316,12 +323,26 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 launches -= 1;
             } else if (walk_kernel) {
                 prof_begin(kExtend, st);
-                if (count_tests)
-                    extend_walk_kernel<R, true><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
-                                                                          (unsigned *)(fetch + b), Q.tally + 2);
+                unsigned *cursor = (unsigned *)(fetch + b);
+                bool launched = false;
+                if constexpr (sizeof(R) == 4) {
+                    if (wide_walk) {
+                        if (count_tests)
+                            extend_walk_kernel<R, true, true><<<g_walk, T, 0, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b,
+                                                                                     Q.perm, cursor, Q.tally + 2);
+                        else
+                            extend_walk_kernel<R, false, true><<<g_walk, T, 0, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b,
+                                                                                      Q.perm, cursor, nullptr);
+                        launched = true;
+                    }
+                }
+                if (launched) {
+                } else if (count_tests)
+                    extend_walk_kernel<R, true, false><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
+                                                                                 cursor, Q.tally + 2);
                 else
-                    extend_walk_kernel<R, false><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
-                                                                           (unsigned *)(fetch + b), nullptr);
+                    extend_walk_kernel<R, false, false><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
+                                                                                  cursor, nullptr);
                 prof_end(st);
                 prof_begin(kShade, st);
                 shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);

@@ -276,19 +276,36 @@ __device__ __forceinline__ void prefetch_tri(const SceneDev &S, int prim) {
 // COUNT (B2RT_PATH_COUNT_TESTS, measurement passes only): per-lane box steps (two slab tests each) and leaf steps
 // (one primitive test each) are tallied into tally[0] / tally[1] — the executed-work and bytes-per-ray figures of
 // bench.py's 1 M-triangle configuration come from these, never from an estimate.
-template <typename R, bool COUNT>
-__global__ void __launch_bounds__(256, sizeof(R) == 4 ? B2RT_WALK_MIN_BLOCKS : 1)
+//
+// WIDE: the box step reads one 4-wide node (128 B: the four grandchild boxes of a binary node, lbvh.cu:widen_kernel)
+// instead of one 64 B binary node, tests four slabs, continues with the nearest child that is hit and stacks the others
+// far to near.  The kernel is bound by the latency of these dependent fetches, so halving their number is what counts;
+// the closest hit is the same (the tie rule lives in test_prim, and a stacked child is never culled late in either
+// form).  No shared-memory top copy: the wide top levels stay in L1.
+#ifndef B2RT_WIDE_MIN_BLOCKS
+#define B2RT_WIDE_MIN_BLOCKS 4
+#endif
+#define B2RT_CSWAP(ta_, ca_, tb_, cb_)                                                  \
+    do {                                                                                \
+        const bool s_ = (tb_) < (ta_);                                                  \
+        const R tl_ = s_ ? (tb_) : (ta_), th_ = s_ ? (ta_) : (tb_);                     \
+        const int cl_ = s_ ? (cb_) : (ca_), ch_ = s_ ? (ca_) : (cb_);                   \
+        (ta_) = tl_; (tb_) = th_; (ca_) = cl_; (cb_) = ch_;                             \
+    } while (0)
+template <typename R, bool COUNT, bool WIDE>
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? (WIDE ? B2RT_WIDE_MIN_BLOCKS : B2RT_WALK_MIN_BLOCKS) : 1)
 extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__restrict__ rd,
                    real4<R> *__restrict__ hit, const unsigned long long *__restrict__ count,
                    const int *__restrict__ perm, unsigned *__restrict__ next, unsigned long long *tally) {
     unsigned n_node = 0, n_leaf = 0;
     extern __shared__ float4 s_top[];
-    stage_top(S, s_top);
+    if (!WIDE) stage_top(S, s_top);
     constexpr int kDone = (int)0x80000000;                       // below every leaf reference (~prim)
+    constexpr int kDepth = WIDE ? kWideStackDepth : kStackDepth;
     const int n = (int)(*count & 0xffffffffULL);
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const R t_min = R(0.001);
-    int stack[kStackDepth];
+    int stack[kDepth];
     int sp = 0, ref = kDone, pos = -1;
     Ray<R> r; r.o = {R(0), R(0), R(0)}; r.d = r.o;
     V3<R> id = r.o;
@@ -322,8 +339,8 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                     ref = (S.n_prims > 0 && !dead_entry) ? S.root : kDone;
                     if (dead_entry) pos = -1;
                     if (S.n_outside > 0 && !dead_entry) {        // rectangles outside the hierarchy: leaves visited first
-                        B2RT_PUSH(S, stack, sp, ref);
-                        for (int p = S.n_outside - 1; p >= 1; --p) B2RT_PUSH(S, stack, sp, ~p);
+                        B2RT_PUSH_N(S, stack, sp, ref, kDepth);
+                        for (int p = S.n_outside - 1; p >= 1; --p) B2RT_PUSH_N(S, stack, sp, ~p, kDepth);
                         ref = ~0;
                     }
                 }
@@ -333,6 +350,34 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
         }
         if ((mn | ml) == 0u) break;                              // nothing in flight and nothing left to fetch
         if (__popc(mn) >= __popc(ml)) {
+            if constexpr (WIDE) {
+                if (ref >= 0) {
+                    if (COUNT) ++n_node;
+                    const float4 *p = S.wide + 8 * (size_t)ref;
+                    const float4 ax = __ldg(p), ay = __ldg(p + 1), az = __ldg(p + 2);
+                    const float4 bx = __ldg(p + 3), by = __ldg(p + 4), bz = __ldg(p + 5), cf = __ldg(p + 6);
+                    constexpr R kMiss = R(3.0e38);
+                    // entry distance of one slot, or kMiss (same slab arithmetic as the binary step below)
+                    auto enter = [&](float lx, float ly, float lz, float hx, float hy, float hz, int c) -> R {
+                        const R x0 = (R(lx) - r.o.x) * id.x, x1 = (R(hx) - r.o.x) * id.x;
+                        const R y0 = (R(ly) - r.o.y) * id.y, y1 = (R(hy) - r.o.y) * id.y;
+                        const R z0 = (R(lz) - r.o.z) * id.z, z1 = (R(hz) - r.o.z) * id.z;
+                        const R tn = max_(max_(min_(x0, x1), min_(y0, y1)), max_(min_(z0, z1), t_min));
+                        const R tf = min_(min_(max_(x0, x1), max_(y0, y1)), min_(max_(z0, z1), best.t));
+                        return (tn <= tf && c != kDone) ? tn : kMiss;
+                    };
+                    int c0 = __float_as_int(cf.x), c1 = __float_as_int(cf.y), c2 = __float_as_int(cf.z), c3 = __float_as_int(cf.w);
+                    R t0 = enter(ax.x, ay.x, az.x, bx.x, by.x, bz.x, c0), t1 = enter(ax.y, ay.y, az.y, bx.y, by.y, bz.y, c1);
+                    R t2 = enter(ax.z, ay.z, az.z, bx.z, by.z, bz.z, c2), t3 = enter(ax.w, ay.w, az.w, bx.w, by.w, bz.w, c3);
+                    B2RT_CSWAP(t0, c0, t1, c1); B2RT_CSWAP(t2, c2, t3, c3);      // ascending by entry distance
+                    B2RT_CSWAP(t0, c0, t2, c2); B2RT_CSWAP(t1, c1, t3, c3);
+                    B2RT_CSWAP(t1, c1, t2, c2);
+                    if (t3 < kMiss) B2RT_PUSH_N(S, stack, sp, c3, kDepth);
+                    if (t2 < kMiss) B2RT_PUSH_N(S, stack, sp, c2, kDepth);
+                    if (t1 < kMiss) B2RT_PUSH_N(S, stack, sp, c1, kDepth);
+                    ref = t0 < kMiss ? c0 : stack[--sp];
+                }
+            } else {
 #pragma unroll
             for (int rep = 0; rep < B2RT_WALK_NODE_STEPS; ++rep) {
             if (ref >= 0) {
@@ -367,6 +412,7 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                 } else if (hl) ref = cl;
                 else if (hr) ref = cr;
                 else ref = stack[--sp];
+            }
             }
             }
         } else if (want_leaf) {

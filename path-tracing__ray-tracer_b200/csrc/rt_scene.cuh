@@ -39,6 +39,7 @@ namespace b2rt {
 #define B2RT_STACK_DEPTH 64
 #endif
 constexpr int kStackDepth = B2RT_STACK_DEPTH;
+constexpr int kWideStackDepth = B2RT_STACK_DEPTH + B2RT_STACK_DEPTH / 2;   // 4-wide walk: up to three pushes per level, half the levels
 constexpr int kScanUnroll = B2RT_SCAN_UNROLL;       // LBVH depth bound: 30 Morton bits + log2(duplicates)
 
 struct SceneDev {
@@ -50,6 +51,7 @@ struct SceneDev {
     const uint32_t *texels;
     const int4 *tex_info;
     const float4 *nodes, *top;
+    const float4 *wide;                // 4-wide nodes (b2rt_lbvh_widen) or nullptr
     int n_top, root;
     int scan_incoherent;
     int n_outside;                     // rectangles [0, n_outside) are not in the hierarchy: tested before every walk
@@ -74,6 +76,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.texels = s->d_texels; d.tex_info = reinterpret_cast<const int4 *>(s->d_tex_info);
     d.nodes = reinterpret_cast<const float4 *>(s->d_bvh_nodes);
     d.top = reinterpret_cast<const float4 *>(s->d_bvh_top);
+    d.wide = reinterpret_cast<const float4 *>(s->d_bvh_wide);
     d.n_top = s->n_bvh_top; d.root = s->bvh_root;
     d.scan_incoherent = s->scan_incoherent;
     d.n_outside = s->bvh_rects_outside ? s->n_rect : 0;
@@ -92,11 +95,12 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
 // closest-hit record: a/b are (u_hit, v_hit) in world units for a rectangle, the barycentrics
 // (u, v) for a triangle, unused for a sphere
 // bounds-checked traversal-stack push (plain store unless B2RT_CHECK)
-#define B2RT_PUSH(S_, stack_, sp_, v_)                                                              \
+#define B2RT_PUSH_N(S_, stack_, sp_, v_, depth_)                                                    \
     do {                                                                                            \
-        if (B2RT_CHECK && (sp_) >= kStackDepth) { if ((S_).check) atomicAdd((S_).check, 1ULL); }    \
+        if (B2RT_CHECK && (sp_) >= (depth_)) { if ((S_).check) atomicAdd((S_).check, 1ULL); }       \
         else (stack_)[(sp_)++] = (v_);                                                              \
     } while (0)
+#define B2RT_PUSH(S_, stack_, sp_, v_) B2RT_PUSH_N(S_, stack_, sp_, v_, kStackDepth)
 
 template <typename R> struct Hit {
     R t, a, b;

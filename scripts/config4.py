@@ -9,7 +9,7 @@ from b200rt import _lib, packer, renderer, scenes
 from b200rt.device import DeviceScene, current_stream_ptr
 from b200rt.scene_api import RenderSettings
 
-kw = dict(W=1920, H=1080, spp=64, depth=4, steps=2, check=4096, top=512, sort=1, fwalk=0, wprim=0, rout=1, rot=1)
+kw = dict(W=1920, H=1080, spp=64, depth=4, steps=2, check=4096, top=512, sort=1, fwalk=0, wprim=0, rout=1, rot=1, wide=1)
 for a in sys.argv[1:]:
     k, v = a.split("="); kw[k] = type(kw[k])(v)
 lib = _lib.load()
@@ -30,6 +30,9 @@ for _ in range(6):
     _lib.check(lib.b2rt_lbvh_build(pk.n_rect, pk.n_sphere, pk.n_tri, ds.rect.data_ptr(), ds.sphere.data_ptr(), ds.tri.data_ptr(),
                                    C.c_float(ds.box_pad), ds.nodes.data_ptr(), ds.top.data_ptr(), kw["top"], meta,
                                    temp.data_ptr(), temp.numel(), current_stream_ptr(dev), (1 if ds.rects_outside else 0) | (0 if kw["rot"] else 2)), "lbvh")
+    if ds.wide is not None:                                   # the 4-wide nodes are part of the build
+        _lib.check(lib.b2rt_lbvh_widen(ds.nodes.data_ptr(), ds.top.data_ptr(), meta[0], meta[2], ds.wide.data_ptr(), ds.wide.numel(),
+                                       current_stream_ptr(dev)), "widen")
     e1.record(); torch.cuda.synchronize()
     times.append(e0.elapsed_time(e1))
 build_ms = float(np.median(times[1:]))
@@ -42,7 +45,7 @@ a_ids, a_rec = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=1, packe
 b_ids, b_rec = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=0, packed=pk)
 same = bool(np.array_equal(a_ids, b_ids) and np.array_equal(a_rec[:, 0], b_rec[:, 0]))
 # ---- path tracing throughput
-r = renderer.B200PathTracer(precision="f32", top_nodes=kw["top"], sort_rays=bool(kw["sort"]), fused_walk=bool(kw["fwalk"]), walk_primary=bool(kw["wprim"]), rects_outside=bool(kw["rout"]), lbvh_rotations=bool(kw["rot"]))
+r = renderer.B200PathTracer(precision="f32", top_nodes=kw["top"], sort_rays=bool(kw["sort"]), fused_walk=bool(kw["fwalk"]), walk_primary=bool(kw["wprim"]), rects_outside=bool(kw["rout"]), lbvh_rotations=bool(kw["rot"]), wide_walk=bool(kw["wide"]))
 st = r.prepare(scene, cam, RenderSettings(kw["W"], kw["H"], kw["spp"], kw["depth"]))
 r.accumulate(st); torch.cuda.synchronize()
 st["counters"].zero_(); lib.b2rt_profile_enable(1)
@@ -63,5 +66,5 @@ print(json.dumps({
     "mpaths_per_s": cnt[0] / dt / 1e6, "mrays_per_s": (cnt[1] + cnt[2]) / dt / 1e6, "rays_per_path": float((cnt[1] + cnt[2]) / cnt[0]),
     "ms_per_step": dt / kw["steps"] * 1e3, "wave": st["wave"],
     "kernel_ms_per_step": {k: ms[i] / kw["steps"] for i, k in enumerate(["raygen", "extend", "bounce", "shadow", "accumulate", "sort"])},
-    "sort_rays": kw["sort"], "fused_walk": kw["fwalk"], "walk_primary": kw["wprim"], "rects_outside": kw["rout"], "lbvh_rotations": kw["rot"],
+    "sort_rays": kw["sort"], "fused_walk": kw["fwalk"], "walk_primary": kw["wprim"], "rects_outside": kw["rout"], "lbvh_rotations": kw["rot"], "wide_walk": kw["wide"],
 }))

@@ -175,16 +175,68 @@ def test_persistent_walk_kernel_equals_fused_walk():
     cam = b.create_camera(16 / 9)
     st = RenderSettings(320, 180, 8, 4)
     out = {}
-    for fused_walk in (False, True):
+    for fused_walk, wide in ((False, True), (False, False), (True, True)):    # 4-wide nodes, binary nodes, fused per-ray walk
         for sort in (True, False):
-            r = renderer.B200PathTracer(precision="f32", rng="pcg", seed=5, fused_walk=fused_walk, sort_rays=sort)
+            r = renderer.B200PathTracer(precision="f32", rng="pcg", seed=5, fused_walk=fused_walk, sort_rays=sort,
+                                        wide_walk=wide)
             acc, cnt = r.render_accum(scene, cam, st)
-            out[(fused_walk, sort)] = (acc, cnt)
-    ref_acc, ref_cnt = out[(True, False)]
+            out[(fused_walk, sort, wide)] = (acc, cnt)
+    ref_acc, ref_cnt = out[(True, False, True)]
     for key, (acc, cnt) in out.items():
         assert np.array_equal(cnt[:4], ref_cnt[:4]), (key, cnt, ref_cnt)
         # per-pixel sums are added in path order inside a wave, which the ray sort does not change (L[slot])
         assert np.array_equal(acc, ref_acc), key
+
+
+def test_wide_nodes_hold_the_grandchildren():
+    """b2rt_lbvh_widen: entry `ref` of the 4-wide array holds exactly the boxes and references of the grandchildren of
+    binary node `ref` (a leaf child stays one slot), and the walk over them counts fewer box steps than the binary walk."""
+    from b200rt import _lib, scenes
+    from b200rt.device import DeviceScene
+    from b200rt.packer import pack_scene
+    scene, b = scenes.heightfield_scene(nx=101, nz=51)              # 10 000 triangles
+    ds = DeviceScene(pack_scene(scene, "numba"), _lib.P_F32, wide_nodes=True)
+    assert ds.wide is not None and ds.struct.d_bvh_wide
+    torch.cuda.synchronize()
+    n_top, n_int = ds.n_top, ds.n_internal
+    nodes = ds.nodes.cpu().numpy().reshape(-1, 16)[:n_int]
+    top = ds.top.cpu().numpy().reshape(-1, 16)[:n_top]
+    wide = ds.wide.cpu().numpy().view(np.float32).reshape(-1, 32)
+    assert wide.shape[0] == n_top + n_int
+
+    def record(ref):
+        rec = top[ref] if ref < n_top else nodes[ref - n_top]
+        refs = rec[12:14].view(np.int32)
+        return ((rec[0:3], rec[3:6], int(refs[0])), (rec[6:9], rec[9:12], int(refs[1])))
+
+    empty = -(1 << 31)
+    seen, frontier = 0, [ds.root]
+    while frontier:                                                  # every wide node the walk can reach from the root
+        ref = frontier.pop()
+        want = []
+        for lo, hi, c in record(ref):
+            want += [(lo, hi, c)] if c < 0 else list(record(c))
+        w = wide[ref]
+        refs = w[24:28].view(np.int32)
+        assert [int(x) for x in refs[:len(want)]] == [c for _, _, c in want]
+        assert all(int(x) == empty for x in refs[len(want):])
+        for k, (lo, hi, c) in enumerate(want):
+            assert np.array_equal(w[[k, 4 + k, 8 + k]], lo) and np.array_equal(w[[12 + k, 16 + k, 20 + k]], hi)
+            if c >= 0:
+                frontier.append(c)
+        seen += 1
+    assert seen > n_int // 4                                         # about half the tree's levels
+    # the counted walk: fewer box steps with the wide nodes, the same leaf tests or fewer, identical results
+    cam = b.create_camera(16 / 9)
+    st = RenderSettings(160, 90, 4, 3)
+    steps = {}
+    for wide_walk in (True, False):
+        r = renderer.B200PathTracer(precision="f32", rng="pcg", seed=2, count_tests=True, wide_walk=wide_walk)
+        acc, cnt = r.render_accum(scene, cam, st)
+        steps[wide_walk] = (acc, cnt)
+    assert np.array_equal(steps[True][0], steps[False][0])
+    assert np.array_equal(steps[True][1][:4], steps[False][1][:4])
+    assert 0 < steps[True][1][8] < 0.75 * steps[False][1][8], (steps[True][1][8:10], steps[False][1][8:10])
 
 
 def test_progressive_accumulation_continues_the_sample_sequence(tmp_path):
