@@ -193,8 +193,7 @@ class DeviceScene:
             # wide_nodes (off by default): 4-wide nodes for the persistent walk kernel of float32 scenes too large for the
             # record scan, derived on the device from the finished tree (128 B per node reference).  Measured on the
             # 1 M-triangle scene: 14.4 instead of 28.8 box steps per ray, identical hits, but 65.0 vs 62.4 ms per step in
-            # the walk kernel — its stalls are the DRAM misses of the bottom levels, which a wider node does not remove
-            # (profiles/r2_c4_wide_nodes_ab.log)
+            # the walk kernel (profiles/r2_c4_wide_nodes_ab.log, r2_c4_walk_kernel_analysis.md)
             self.wide = None
             if wide_nodes and precision == _lib.P_F32 and not scan_ok and self.n_internal > 0:
                 wb = C.c_size_t(0)

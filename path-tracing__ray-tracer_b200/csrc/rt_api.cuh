@@ -217,7 +217,7 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     const bool count_tests = (a.flags & 64) != 0;
     // float32 scenes that carry 4-wide nodes (b2rt_lbvh_widen) walk those: half the dependent node fetches per ray
     const bool wide_walk = walk_kernel && S.wide != nullptr && !(a.flags & 512);
-    const size_t smem_walk = wide_walk ? 0 : smem;
+    const size_t smem_walk = wide_walk ? 0 : walk_smem_bytes(S);
     const void *k_walk = count_tests ? (const void *)extend_walk_kernel<R, true, false> : (const void *)extend_walk_kernel<R, false, false>;
     if constexpr (sizeof(R) == 4) {
         if (wide_walk) k_walk = count_tests ? (const void *)extend_walk_kernel<R, true, true> : (const void *)extend_walk_kernel<R, false, true>;
@@ -338,11 +338,11 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 }
                 if (launched) {
                 } else if (count_tests)
-                    extend_walk_kernel<R, true, false><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
-                                                                                 cursor, Q.tally + 2);
+                    extend_walk_kernel<R, true, false><<<g_walk, T, smem_walk, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
+                                                                                      cursor, Q.tally + 2);
                 else
-                    extend_walk_kernel<R, false, false><<<g_walk, T, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
-                                                                                  cursor, nullptr);
+                    extend_walk_kernel<R, false, false><<<g_walk, T, smem_walk, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
+                                                                                       cursor, nullptr);
                 prof_end(st);
                 prof_begin(kShade, st);
                 shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);

@@ -25,6 +25,33 @@ __device__ __forceinline__ double4 ldg4(const double4 *p) {
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// L2 residency hints for the hierarchy of large scenes (measurement switch): bit 0 = the node loads
+// of the persistent walk kernel, bit 1 = the triangle records, bit 2 = the walk kernel's hit records leave with a
+// streaming store.  The loads carry an L2::evict_last policy so that the gigabytes of queue records streaming past do not
+// push nodes and triangles out.
+#ifndef B2RT_L2_HINT
+#define B2RT_L2_HINT 0
+#endif
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg4_keep(const float4 *p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double4 ldg4_keep(const double4 *p, unsigned long long) { return ldg4(p); }
+
+// 256-bit read-only load (sm_100: LDG.E.256): one 32 B sector per lane in ONE L1 data-pipe wavefront where two
+// LDG.128 to the same sector cost two.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg8(const float4 *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
 // streaming (evict-first) access for queue records that are touched exactly once per kernel, so they do
 // not push the small scene tables out of L1/L2
 __device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }

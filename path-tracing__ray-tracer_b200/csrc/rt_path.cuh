@@ -292,6 +292,32 @@ __device__ __forceinline__ void prefetch_tri(const SceneDev &S, int prim) {
         const int cl_ = s_ ? (cb_) : (ca_), ch_ = s_ ? (ca_) : (cb_);                   \
         (ta_) = tl_; (tb_) = th_; (ca_) = cl_; (cb_) = ch_;                             \
     } while (0)
+// Two switches that cut the L1 data-pipe work of the binary walk, both MEASURED AND OFF (profiles/r2_c4_walk_kernel_analysis.md:
+// ncu shows the L1 data pipe at 89.6 % of its wavefront rate on the 1 M-triangle scene, yet every combination below lands
+// on the same 65.16 ms per step as the plain kernel, 65.1):
+//   B2RT_WALK_LDG256      the 64 B node comes in as two 256-bit loads (sm_100 LDG.E.256) instead of four 128-bit ones;
+//   B2RT_WALK_SMEM_STACK  the first N traversal-stack entries live in shared memory as [entry][thread] (every lane has its
+//                         own bank whatever its depth: a push or pop is one wavefront and never leaves the SM, where the
+//                         per-thread local array misses L1 for 97 % of its sectors).  Deeper entries fall back to the
+//                         local array; the shared-memory top copy shrinks to B2RT_WALK_TOP_STAGE nodes to make room (the
+//                         rest of the top levels is read from S.top).
+#ifndef B2RT_WALK_LDG256
+#define B2RT_WALK_LDG256 0
+#endif
+#ifndef B2RT_WALK_SMEM_STACK
+#define B2RT_WALK_SMEM_STACK 0
+#endif
+#ifndef B2RT_WALK_TOP_STAGE
+#define B2RT_WALK_TOP_STAGE 128
+#endif
+constexpr int kWalkSmemStack = B2RT_WALK_SMEM_STACK < kStackDepth ? B2RT_WALK_SMEM_STACK : kStackDepth;
+inline __host__ __device__ int walk_top_staged(int n_top) {
+    return (kWalkSmemStack > 0 && n_top > B2RT_WALK_TOP_STAGE) ? B2RT_WALK_TOP_STAGE : n_top;
+}
+// dynamic shared memory of the binary walk kernel: staged top nodes + the shared part of the stacks (256 threads)
+inline size_t walk_smem_bytes(const SceneDev &S) {
+    return (size_t)walk_top_staged(S.n_top) * 64 + (size_t)kWalkSmemStack * 256 * sizeof(int);
+}
 template <typename R, bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(256, sizeof(R) == 4 ? (WIDE ? B2RT_WIDE_MIN_BLOCKS : B2RT_WALK_MIN_BLOCKS) : 1)
 extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__restrict__ rd,
@@ -299,25 +325,42 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                    const int *__restrict__ perm, unsigned *__restrict__ next, unsigned long long *tally) {
     unsigned n_node = 0, n_leaf = 0;
     extern __shared__ float4 s_top[];
-    if (!WIDE) stage_top(S, s_top);
+    const int n_stage = WIDE ? 0 : walk_top_staged(S.n_top);
+    if (!WIDE) {
+        for (int i = threadIdx.x; i < 4 * n_stage; i += blockDim.x) s_top[i] = __ldg(S.top + i);
+        __syncthreads();
+    }
     constexpr int kDone = (int)0x80000000;                       // below every leaf reference (~prim)
     constexpr int kDepth = WIDE ? kWideStackDepth : kStackDepth;
+    constexpr int kShared = WIDE ? 0 : kWalkSmemStack;           // stack entries [0, kShared) live in shared memory
     const int n = (int)(*count & 0xffffffffULL);
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const R t_min = R(0.001);
-    int stack[kDepth];
+    int stack[kDepth - kShared > 0 ? kDepth - kShared : 1];
+    int *s_stack = reinterpret_cast<int *>(s_top + 4 * n_stage) + threadIdx.x;     // entry k at s_stack[k * 256]
     int sp = 0, ref = kDone, pos = -1;
     Ray<R> r; r.o = {R(0), R(0), R(0)}; r.d = r.o;
     V3<R> id = r.o;
     Hit<R> best; best.t = R(0); best.a = R(0); best.b = R(0); best.prim = -1;
     bool exhausted = false;                                      // warp-uniform: the queue has no rays left
+    auto push = [&](int v) {
+        if (B2RT_CHECK && sp >= kDepth) { if (S.check) atomicAdd(S.check, 1ULL); return; }
+        if (kShared > 0 && sp < kShared) s_stack[sp * 256] = v; else stack[sp - kShared] = v;
+        ++sp;
+    };
+    auto pop = [&]() -> int {
+        --sp;
+        return (kShared > 0 && sp < kShared) ? s_stack[sp * 256] : stack[sp - kShared];
+    };
     for (;;) {
         const bool want_node = ref >= 0, want_leaf = ref < 0 && ref != kDone;
         const unsigned mn = __ballot_sync(0xffffffffu, want_node), ml = __ballot_sync(0xffffffffu, want_leaf);
         const unsigned idle = ~(mn | ml);
         if (!exhausted && (__popc(idle) >= B2RT_WALK_REFILL)) {
-            if (ref == kDone && pos >= 0)
-                hit[pos] = Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b);
+            if (ref == kDone && pos >= 0) {
+                const real4<R> rec = Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b);
+                if constexpr ((B2RT_L2_HINT & 4) != 0) st_stream(hit + pos, rec); else hit[pos] = rec;
+            }
             // (taking the indices in per-warp chunks of 32 / 128 / 512 instead was measured at 63.3 / 64.4 / 69.7 ms per
             // step against 62.5: this kernel is latency-bound, not bound by the cursor's atomic unit)
             unsigned base = 0;
@@ -333,14 +376,14 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                     r.o = xyz<R>(a); r.d = xyz<R>(b);
                     id = {rcp_(r.d.x), rcp_(r.d.y), rcp_(r.d.z)};
                     best.t = R(1000000.0); best.prim = -1; best.a = R(0); best.b = R(0);
-                    stack[0] = kDone; sp = 1;
+                    sp = 0; push(kDone);
                     // a dead entry (unused remainder of a producer warp's chunk, slot word -1) is no ray at all
                     const bool dead_entry = (int)unpack_u<R>(a.w) < 0;
                     ref = (S.n_prims > 0 && !dead_entry) ? S.root : kDone;
                     if (dead_entry) pos = -1;
                     if (S.n_outside > 0 && !dead_entry) {        // rectangles outside the hierarchy: leaves visited first
-                        B2RT_PUSH_N(S, stack, sp, ref, kDepth);
-                        for (int p = S.n_outside - 1; p >= 1; --p) B2RT_PUSH_N(S, stack, sp, ~p, kDepth);
+                        push(ref);
+                        for (int p = S.n_outside - 1; p >= 1; --p) push(~p);
                         ref = ~0;
                     }
                 }
@@ -372,10 +415,10 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                     B2RT_CSWAP(t0, c0, t1, c1); B2RT_CSWAP(t2, c2, t3, c3);      // ascending by entry distance
                     B2RT_CSWAP(t0, c0, t2, c2); B2RT_CSWAP(t1, c1, t3, c3);
                     B2RT_CSWAP(t1, c1, t2, c2);
-                    if (t3 < kMiss) B2RT_PUSH_N(S, stack, sp, c3, kDepth);
-                    if (t2 < kMiss) B2RT_PUSH_N(S, stack, sp, c2, kDepth);
-                    if (t1 < kMiss) B2RT_PUSH_N(S, stack, sp, c1, kDepth);
-                    ref = t0 < kMiss ? c0 : stack[--sp];
+                    if (t3 < kMiss) push(c3);
+                    if (t2 < kMiss) push(c2);
+                    if (t1 < kMiss) push(c1);
+                    ref = t0 < kMiss ? c0 : pop();
                 }
             } else {
 #pragma unroll
@@ -383,12 +426,19 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
             if (ref >= 0) {
                 if (COUNT) ++n_node;
                 float4 n0, n1, n2, n3;
-                if (ref < S.n_top) {
+                if (ref < n_stage) {
                     const float4 *p = s_top + 4 * ref;
                     n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
                 } else {
-                    const float4 *p = S.nodes + 4 * (size_t)(ref - S.n_top);
-                    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
+                    const float4 *p = ref < S.n_top ? S.top + 4 * ref : S.nodes + 4 * (size_t)(ref - S.n_top);
+                    if constexpr (B2RT_WALK_LDG256 != 0) {
+                        ldg8(p, n0, n1); ldg8(p + 2, n2, n3);
+                    } else if constexpr ((B2RT_L2_HINT & 1) != 0) {
+                        const unsigned long long pol = l2_keep_policy();
+                        n0 = ldg4_keep(p, pol); n1 = ldg4_keep(p + 1, pol); n2 = ldg4_keep(p + 2, pol); n3 = ldg4_keep(p + 3, pol);
+                    } else {
+                        n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
+                    }
                 }
                 // slab distances in the subtraction form the builder's box pad is sized for.  (The one-FMA form
                 // b * (1/d) - o * (1/d) is NOT conservative: measured 16 differing closest hits in 72.7 M rays on the
@@ -407,21 +457,24 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                 const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
                 if (hl && hr) {
                     const bool swap = tr < tl;
-                    B2RT_PUSH(S, stack, sp, swap ? cl : cr);
+                    push(swap ? cl : cr);
                     ref = swap ? cr : cl;
                 } else if (hl) ref = cl;
                 else if (hr) ref = cr;
-                else ref = stack[--sp];
+                else ref = pop();
             }
             }
             }
         } else if (want_leaf) {
             if (COUNT) ++n_leaf;
             test_prim<R, false>(S, ~ref, r, t_min, best);
-            ref = stack[--sp];
+            ref = pop();
         }
     }
-    if (pos >= 0) hit[pos] = Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b);
+    if (pos >= 0) {
+        const real4<R> rec = Real4<R>::make(best.t, pack_int<R>((int64_t)best.prim), best.a, best.b);
+        if constexpr ((B2RT_L2_HINT & 4) != 0) st_stream(hit + pos, rec); else hit[pos] = rec;
+    }
     if (COUNT) { warp_flush(tally, n_node); warp_flush(tally + 1, n_leaf); }
 }
 

@@ -179,7 +179,13 @@ template <typename R>
 __device__ __forceinline__ bool hit_tri(const SceneDev &S, int i, const Ray<R> &r, R t_min, R t_far, bool allow_eq,
                                         R &t_out, R &u_out, R &v_out) {
     const real4<R> *q = reinterpret_cast<const real4<R> *>(S.tri) + 3 * i;
-    V3<R> v0 = xyz<R>(ldg4(q)), e1 = xyz<R>(ldg4(q + 1)), e2 = xyz<R>(ldg4(q + 2));
+    V3<R> v0, e1, e2;
+    if constexpr ((B2RT_L2_HINT & 2) != 0 && sizeof(R) == 4) {
+        const unsigned long long pol = l2_keep_policy();
+        v0 = xyz<R>(ldg4_keep(q, pol)); e1 = xyz<R>(ldg4_keep(q + 1, pol)); e2 = xyz<R>(ldg4_keep(q + 2, pol));
+    } else {
+        v0 = xyz<R>(ldg4(q)); e1 = xyz<R>(ldg4(q + 1)); e2 = xyz<R>(ldg4(q + 2));
+    }
     V3<R> h = cross(r.d, e2);
     R a = dot(e1, h);
     if constexpr (sizeof(R) == 4) {

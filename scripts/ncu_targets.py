@@ -24,6 +24,10 @@ elif which == "c4":
     scene, b4 = scenes.heightfield_scene(); cam = b4.create_camera(1920 / 1080)
     r = renderer.B200PathTracer(precision="f32")
     r.render(scene, cam, RenderSettings(1920, 1080, 8, 4))
+elif which == "c4big":                       # the bench's wave size (32 spp per wave): one walk-kernel launch at full occupancy of the queues
+    scene, b4 = scenes.heightfield_scene(); cam = b4.create_camera(1920 / 1080)
+    r = renderer.B200PathTracer(precision="f32")
+    r.render(scene, cam, RenderSettings(1920, 1080, 32, 4))
 elif which == "c3":
     scene = b.build_scene(); cam = b.create_camera(1920 / 1080)
     renderer.B200TextureRaytracer(precision="f32").render(scene, cam, RenderSettings(1920, 1080, 16, 6))
