@@ -356,6 +356,45 @@ def extra_c4(dev, steps: int = 2):
     return out
 
 
+def extra_c4_node_formats(dev, steps: int = 2):
+    """The persistent walk kernel of config 4 on its three node formats — binary 64 B (default), quantised 32 B
+    (``quant_walk``), 4-wide 128 B (``wide_walk``): float sums of a 960x540 x 4 spp x depth 4 render compared bit for bit
+    with the default, then the walk kernel's ms per 1080p x 64 spp x depth 4 step (profiles/r2_c4_walk_kernel_analysis.md)."""
+    import numpy as np
+    import torch
+    from b200rt import _lib, renderer, scenes
+    from b200rt.scene_api import RenderSettings
+    lib = _lib.load()
+    scene, b = scenes.heightfield_scene()
+    cam = b.create_camera(1920 / 1080)
+    out, ref, ws = {}, None, None
+    for name, kw in (("binary_64B", {}), ("quantised_32B", {"quant_walk": True}), ("wide_128B", {"wide_walk": True})):
+        r = renderer.B200PathTracer(precision="f32", seed=3, device=dev, distributed=False, **kw)
+        acc, cnt = r.render_accum(scene, cam, RenderSettings(960, 540, 4, 4))
+        if ref is None:
+            ref = (acc, cnt)
+        same = bool(np.array_equal(acc, ref[0]) and np.array_equal(cnt[:4], ref[1][:4]))
+        if ws is not None:
+            r._ws = ws
+        st = r.prepare(scene, cam, RenderSettings(1920, 1080, 64, 4))
+        ws = r._ws
+        r.accumulate(st); torch.cuda.synchronize(dev)
+        lib.b2rt_profile_enable(1)
+        ms = (C.c_double * 8)(); nl = (C.c_int64 * 8)()
+        lib.b2rt_profile_read(ms, nl)
+        e0, e1 = _events()
+        e0.record()
+        for _ in range(steps):
+            r.accumulate(st)
+        e1.record(); torch.cuda.synchronize(dev)
+        lib.b2rt_profile_read(ms, nl)
+        lib.b2rt_profile_enable(0)
+        out[name] = {"sums_identical_to_binary": same, "walk_kernel_ms_per_step": ms[1] / steps,
+                     "ms_per_step": e0.elapsed_time(e1) / steps}
+        del r, st
+    return out
+
+
 def extra_c5(scene, builder, dev, rank, world, local):
     """BASELINE config 5: 4K (3840x2160) Cornell box, 4096 spp, depth 8, spp split across the ranks + one NCCL reduce."""
     import torch
@@ -592,7 +631,8 @@ def main():
             for name, fn in (("c2_f64_parity", lambda: extra_c2_f64(scene, camera, dev)),
                              ("c3_whitted_texture", lambda: extra_c3(scene, builder, dev)),
                              ("c1_whitted_cpu_semantics", lambda: extra_c1(dev)),
-                             ("c4_heightfield_1m_triangles", lambda: extra_c4(dev))):
+                             ("c4_heightfield_1m_triangles", lambda: extra_c4(dev)),
+                             ("c4_walk_node_formats", lambda: extra_c4_node_formats(dev))):
                 t0 = time.perf_counter()
                 try:
                     extras[name] = fn()

@@ -150,6 +150,10 @@ typedef struct b2rt_scene {
      * n_internal)].  The persistent walk kernel that traces the incoherent rays (bounce >= 1) of float32 scenes too large
      * for the record scan reads these instead of d_bvh_nodes: half the dependent fetches per ray. */
     const void *d_bvh_wide;
+    /* Optional (ABI 3; NULL: not used): quantised binary nodes written by b2rt_lbvh_quantize, 32 B header + 32 B per child
+     * reference.  When present the persistent walk kernel reads these in preference to d_bvh_wide / d_bvh_nodes: a node is
+     * two 16-byte loads instead of four. */
+    const void *d_bvh_quant;
 } b2rt_scene;
 
 const char *b2rt_last_error(void);
@@ -210,6 +214,15 @@ int b2rt_lbvh_build(int32_t n_rect, int32_t n_sphere, int32_t n_tri,
 int b2rt_lbvh_wide_bytes(int32_t n_top, int32_t n_internal, size_t *h_bytes);
 int b2rt_lbvh_widen(const void *d_nodes, const void *d_top, int32_t n_top, int32_t n_internal, void *d_wide_out,
                     size_t wide_bytes, void *stream);
+/* Quantised binary nodes from a finished hierarchy, for the persistent walk kernel: both child boxes of node `ref` as
+ * 16-bit cell indices on a 65536^3 grid over [h_lo, h_hi] (the bounds of ALL primitives incl. the box pad; boxes outside are
+ * clamped to the last cell, which is right for the far-away placeholders of B2RT_LBVH_RECTS_OUTSIDE and wrong for
+ * anything else), every face moved outward by one whole cell on top of the outward rounding so that the float32
+ * dequantisation in the kernel stays conservative.  Layout: 2 float4 header (base.xyz, 0) (cell.xyz, 0), then per
+ * reference 8 words: L.x L.y L.z R.x R.y R.z as lo | hi << 16, ref L, ref R.  Asynchronous on the stream. */
+int b2rt_lbvh_quant_bytes(int32_t n_top, int32_t n_internal, size_t *h_bytes);
+int b2rt_lbvh_quantize(const void *d_nodes, const void *d_top, int32_t n_top, int32_t n_internal, const float *h_lo,
+                       const float *h_hi, void *d_quant_out, size_t quant_bytes, void *stream);
 /* flags for b2rt_lbvh_build */
 #define B2RT_LBVH_NO_ROTATIONS 2  /* skip the bottom-up tree-rotation pass (measurement switch) */
 #define B2RT_LBVH_RECTS_OUTSIDE 1 /* the rectangles get no place in the hierarchy (set b2rt_scene.bvh_rects_outside too: every

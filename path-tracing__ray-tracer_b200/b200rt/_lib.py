@@ -20,6 +20,7 @@ EXPORTS = [
     "b2rt_profile_enable", "b2rt_profile_read", "b2rt_fp32_peak", "b2rt_reduce_resolve", "b2rt_expand_rgb8",
     "b2rt_scene_prepare_bytes", "b2rt_scene_prepare", "b2rt_scene_prepare_host",
     "b2rt_check_enabled", "b2rt_check_read", "b2rt_lbvh_wide_bytes", "b2rt_lbvh_widen",
+    "b2rt_lbvh_quant_bytes", "b2rt_lbvh_quantize",
 ]
 ABI_VERSION = 3
 
@@ -52,7 +53,7 @@ class SceneStruct(C.Structure):
         ("n_bvh_top", C.c_int32), ("bvh_root", C.c_int32), ("scan_incoherent", C.c_int32), ("n_scan_prims", C.c_int32), ("d_scan_prims", C.c_void_p), ("d_occluder_hint", C.c_void_p), ("ray_sort_extent", C.c_float),
         ("n_scan_loose", C.c_int32), ("n_scan_boxes", C.c_int32), ("bvh_rects_outside", C.c_int32),
         ("d_surface_records", C.c_void_p), ("bounds_lo", C.c_float * 3), ("bounds_hi", C.c_float * 3),
-        ("d_bvh_wide", C.c_void_p),
+        ("d_bvh_wide", C.c_void_p), ("d_bvh_quant", C.c_void_p),
     ]
 
 
@@ -83,6 +84,8 @@ def load():
     lib.b2rt_lbvh_build.argtypes = [i32, i32, i32, vp, vp, vp, C.c_float, vp, vp, i32, C.POINTER(i32), vp, sz, vp, i32]
     lib.b2rt_lbvh_wide_bytes.argtypes = [i32, i32, C.POINTER(sz)]
     lib.b2rt_lbvh_widen.argtypes = [vp, vp, i32, i32, vp, sz, vp]
+    lib.b2rt_lbvh_quant_bytes.argtypes = [i32, i32, C.POINTER(sz)]
+    lib.b2rt_lbvh_quantize.argtypes = [vp, vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, sz, vp]
     lib.b2rt_primary_hits.argtypes = [SP, C.POINTER(dbl), i32, i32, dbl, dbl, dbl, dbl, i32, vp, vp, vp]
     lib.b2rt_trace_rays.argtypes = [SP, i32, vp, vp, dbl, dbl, i32, i32, vp, vp, vp]
     lib.b2rt_render_whitted_cpu.argtypes = [SP, C.POINTER(dbl), i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(dbl), vp, vp]

@@ -135,9 +135,11 @@ class _B200Base(BaseRenderer):
 
     def __init__(self, name: str, precision="f32", device=None, top_nodes: int = 512, scan_max_prims: int = 64,
                  occluder_hints: bool = True, scan_boxes: bool = True, surface_records: bool = True,
-                 rects_outside: bool = True, lbvh_rotations: bool = True, wide_nodes: bool = False):
+                 rects_outside: bool = True, lbvh_rotations: bool = True, wide_nodes: bool = False,
+                 quant_nodes: bool = False):
         super().__init__(name)
         self.wide_nodes = wide_nodes
+        self.quant_nodes = quant_nodes
         self.surface_records = surface_records
         self.rects_outside = rects_outside
         self.lbvh_rotations = lbvh_rotations
@@ -175,7 +177,7 @@ class _B200Base(BaseRenderer):
         # the device scene (LBVH, derived records) is a function of the packed bytes and these options: kept while the
         # packed scene is the same object (= unchanged value signature); its inputs are still re-sent every call
         key = (id(packed), self.precision, str(self.device), self.top_nodes, reach, self.scan_max_prims, self.occluder_hints,
-               self.scan_boxes, self.surface_records, self.rects_outside, self.lbvh_rotations, self.wide_nodes)
+               self.scan_boxes, self.surface_records, self.rects_outside, self.lbvh_rotations, self.wide_nodes, self.quant_nodes)
         if self._ds_key == key and self._ds is not None:
             ds = self._ds
             ds.reupload(dev_tex)
@@ -184,7 +186,8 @@ class _B200Base(BaseRenderer):
                              textures_dev=dev_tex, scan_max_prims=self.scan_max_prims,
                              occluder_hints=self.occluder_hints, scan_boxes=self.scan_boxes,
                              surface_records=self.surface_records, rects_outside=self.rects_outside,
-                             lbvh_rotations=self.lbvh_rotations, wide_nodes=self.wide_nodes)
+                             lbvh_rotations=self.lbvh_rotations, wide_nodes=self.wide_nodes,
+                             quant_nodes=self.quant_nodes)
             self._ds, self._ds_key = ds, key
         ds.cam = cam
         ds.h2d_total = ds.h2d_bytes() + self._tex_cache.uploaded_bytes
@@ -222,11 +225,12 @@ class B200PathTracer(_B200Base):
                  scan_boxes: bool = True, primary_walk: bool = False, surface_records: bool = True,
                  fused_walk: bool = False, walk_primary: bool = False, rects_outside: bool = True,
                  lbvh_rotations: bool = True, distributed: bool = True, count_tests: bool = False,
-                 primary_masks: bool = True, split_bounce: bool = True, wide_walk: bool = False):
-        # wide_walk: build 4-wide nodes and let the persistent walk kernel use them (measured slower on the 1 M-triangle
-        # scene, see device.DeviceScene; the results are identical)
+                 primary_masks: bool = True, split_bounce: bool = True, wide_walk: bool = False,
+                 quant_walk: bool = False):
+        # wide_walk / quant_walk: build 4-wide (128 B) or quantised (32 B) nodes and let the persistent walk kernel of large
+        # scenes use them instead of the 64 B binary nodes (identical results; see device.DeviceScene and DESIGN section 8)
         super().__init__("b200_path_tracer", precision, device, top_nodes, scan_max_prims, occluder_hints, scan_boxes,
-                         surface_records, rects_outside, lbvh_rotations, wide_nodes=wide_walk)
+                         surface_records, rects_outside, lbvh_rotations, wide_nodes=wide_walk, quant_nodes=quant_walk)
         self.flags = ((0 if fused else 1) | (0 if sort_rays else 2) | (4 if primary_walk else 0) | (8 if fused_walk else 0)
                       | (32 if walk_primary else 0) | (64 if count_tests else 0) | (0 if primary_masks else 128)
                       | (0 if split_bounce else 256) | (0 if wide_walk else 512))

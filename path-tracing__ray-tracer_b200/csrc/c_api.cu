@@ -172,6 +172,19 @@ int b2rt_lbvh_widen(const void *d_nodes, const void *d_top, int32_t n_top, int32
     return 0;
 }
 
+int b2rt_lbvh_quant_bytes(int32_t n_top, int32_t n_internal, size_t *h_bytes) {
+    *h_bytes = b2rt::lbvh_quant_bytes(n_top, n_internal);
+    return 0;
+}
+
+int b2rt_lbvh_quantize(const void *d_nodes, const void *d_top, int32_t n_top, int32_t n_internal, const float *h_lo,
+                       const float *h_hi, void *d_quant_out, size_t quant_bytes, void *stream) {
+    cudaError_t e = b2rt::lbvh_quantize((const float4 *)d_nodes, (const float4 *)d_top, n_top, n_internal, h_lo, h_hi,
+                                        d_quant_out, quant_bytes, S(stream));
+    if (e) return fail("b2rt_lbvh_quantize", e);
+    return 0;
+}
+
 static int check_scene(const b2rt_scene *s) {
     if (!s) return fail_msg("scene is NULL");
     if (s->struct_size != sizeof(b2rt_scene) || s->abi_version != B2RT_ABI_VERSION) {

@@ -459,6 +459,35 @@ __global__ void widen_kernel(int n_refs, int n_top, const float4 *__restrict__ n
     w[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Quantised binary nodes for the persistent walk kernel (rt_path.cuh:extend_walk_kernel<.., 2>): entry `ref` holds the two
+// child boxes of node `ref` as 16-bit cell indices on a grid (base, cell) over the scene bounds + the two references,
+// 32 B instead of 64.  lo faces round down and move one more cell out, hi faces round up and one more cell out: the
+// kernel dequantises with one float32 FFMA per plane (error ~0.02 cells), so the box it tests always contains the
+// float32 box of the tree.  Indices clamp to [0, 65535]: only the far-away placeholder boxes of rectangles kept outside
+// the hierarchy lie beyond the grid, and they collapse into its last cell.
+__global__ void quantize_kernel(int n_refs, int n_top, const float4 *__restrict__ nodes, const float4 *__restrict__ top,
+                                float3 base, float3 cell, uint4 *__restrict__ out) {
+    const int ref = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ref == 0) {
+        reinterpret_cast<float4 *>(out)[0] = make_float4(base.x, base.y, base.z, 0.f);
+        reinterpret_cast<float4 *>(out)[1] = make_float4(cell.x, cell.y, cell.z, 0.f);
+    }
+    if (ref >= n_refs) return;
+    const float4 *p = ref < n_top ? top + 4 * (size_t)ref : nodes + 4 * (size_t)(ref - n_top);
+    const float4 n0 = p[0], n1 = p[1], n2 = p[2], n3 = p[3];
+    auto pack = [](float lo, float hi, float b, float c) -> unsigned {
+        const float ql = fminf(fmaxf(floorf((lo - b) / c) - 1.f, 0.f), 65535.f);
+        const float qh = fminf(fmaxf(ceilf((hi - b) / c) + 1.f, 0.f), 65535.f);
+        return (unsigned)ql | ((unsigned)qh << 16);
+    };
+    uint4 a, b;
+    a.x = pack(n0.x, n0.w, base.x, cell.x); a.y = pack(n0.y, n1.x, base.y, cell.y); a.z = pack(n0.z, n1.y, base.z, cell.z);
+    a.w = pack(n1.z, n2.y, base.x, cell.x); b.x = pack(n1.w, n2.z, base.y, cell.y); b.y = pack(n2.x, n2.w, base.z, cell.z);
+    b.z = (unsigned)__float_as_int(n3.x); b.w = (unsigned)__float_as_int(n3.y);
+    out[2 + 2 * (size_t)ref] = a;
+    out[3 + 2 * (size_t)ref] = b;
+}
+
 inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct TempLayout {
@@ -572,6 +601,35 @@ cudaError_t lbvh_widen(const float4 *nodes, const float4 *top, int n_top, int n_
     const int n_refs = n_top + n_internal;
     if (n_internal == 0) return cudaSuccess;                  // no internal node: the root reference is a leaf (or nothing)
     widen_kernel<<<(n_refs + 255) / 256, 256, 0, stream>>>(n_refs, n_top, nodes, top, wide);
+    return cudaGetLastError();
+}
+
+size_t lbvh_quant_bytes(int n_top, int n_internal) {
+    const size_t n = (size_t)(n_top > 0 ? n_top : 0) + (size_t)(n_internal > 0 ? n_internal : 0);
+    return 32 + (n > 0 ? n : 1) * 32;
+}
+
+cudaError_t lbvh_quantize(const float4 *nodes, const float4 *top, int n_top, int n_internal, const float *lo, const float *hi,
+                          void *quant, size_t quant_bytes, cudaStream_t stream) {
+    if (n_top < 0 || n_internal < 0 || !lo || !hi || !quant || (n_internal > 0 && !nodes) || (n_top > 0 && !top))
+        return cudaErrorInvalidValue;
+    if (quant_bytes < lbvh_quant_bytes(n_top, n_internal)) return cudaErrorInvalidValue;
+    // grid: 65536 cells per axis, the bounds occupy cells [2, 65533] so that the outward cell never clamps
+    float ext_max = 1e-3f;
+    for (int k = 0; k < 3; ++k) {
+        if (!(hi[k] >= lo[k])) return cudaErrorInvalidValue;
+        ext_max = fmaxf(ext_max, fmaxf(hi[k] - lo[k], fmaxf(fabsf(lo[k]), fabsf(hi[k])) * 1e-6f));
+    }
+    float b[3], c[3];
+    for (int k = 0; k < 3; ++k) {
+        const float ext = fmaxf(hi[k] - lo[k], ext_max * 1e-6f);          // a flat axis still gets a non-zero cell
+        c[k] = ext / 65531.f;
+        b[k] = lo[k] - 2.f * c[k];
+    }
+    const int n_refs = n_top + n_internal;
+    quantize_kernel<<<(n_refs > 0 ? n_refs + 255 : 256) / 256, 256, 0, stream>>>(n_internal > 0 ? n_refs : 0, n_top, nodes, top,
+                                                                                make_float3(b[0], b[1], b[2]),
+                                                                                make_float3(c[0], c[1], c[2]), (uint4 *)quant);
     return cudaGetLastError();
 }
 

@@ -13,4 +13,8 @@ cudaError_t lbvh_build(int n_rect, int n_sphere, int n_tri, const float4 *rect, 
 size_t lbvh_wide_bytes(int n_top, int n_internal);
 cudaError_t lbvh_widen(const float4 *nodes, const float4 *top, int n_top, int n_internal, float4 *wide, size_t wide_bytes,
                        cudaStream_t stream);
+// quantised 32 B binary nodes on a 16-bit grid over [lo, hi] (host float[3] each); see lbvh.cu:quantize_kernel
+size_t lbvh_quant_bytes(int n_top, int n_internal);
+cudaError_t lbvh_quantize(const float4 *nodes, const float4 *top, int n_top, int n_internal, const float *lo, const float *hi,
+                          void *quant, size_t quant_bytes, cudaStream_t stream);
 }  // namespace b2rt

@@ -140,6 +140,20 @@ template <typename R> size_t Api<R>::path_workspace_bytes(int W, int H, int spp_
     return PathLayout<R>::make(W, H, spp_per_wave, max_depth).total;
 }
 
+template <typename R, int NODES> inline const void *walk_kernel_ptr(bool count) {
+    return count ? (const void *)extend_walk_kernel<R, true, NODES> : (const void *)extend_walk_kernel<R, false, NODES>;
+}
+template <typename R, int NODES>
+inline void launch_walk(bool count, int grid, int block, size_t smem, cudaStream_t st, const SceneDev &S, const PathQueues<R> &Q,
+                        int buf, int b, unsigned *cursor) {
+    if (count)
+        extend_walk_kernel<R, true, NODES><<<grid, block, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm, cursor,
+                                                                      Q.tally + 2);
+    else
+        extend_walk_kernel<R, false, NODES><<<grid, block, smem, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm, cursor,
+                                                                       nullptr);
+}
+
 template <typename R, typename Rng>
 cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathArgs &a, cudaStream_t st) {
     SceneDev S = make_scene_dev(s);
@@ -215,12 +229,15 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
     // large scenes: incoherent bounces run the persistent walk kernel + the wavefront shade stage
     const bool walk_kernel = fused && sizeof(R) == 4 && !S.scan_incoherent && !(a.flags & 8);
     const bool count_tests = (a.flags & 64) != 0;
-    // float32 scenes that carry 4-wide nodes (b2rt_lbvh_widen) walk those: half the dependent node fetches per ray
-    const bool wide_walk = walk_kernel && S.wide != nullptr && !(a.flags & 512);
-    const size_t smem_walk = wide_walk ? 0 : walk_smem_bytes(S);
-    const void *k_walk = count_tests ? (const void *)extend_walk_kernel<R, true, false> : (const void *)extend_walk_kernel<R, false, false>;
+    // node format of the walk kernel: float32 scenes that carry quantised 32 B nodes (b2rt_lbvh_quantize) or 4-wide nodes
+    // (b2rt_lbvh_widen) walk those unless B2RT_PATH_BINARY_WALK asks for the plain 64 B nodes
+    int walk_nodes = 0;
+    if (walk_kernel && sizeof(R) == 4 && !(a.flags & 512)) walk_nodes = S.quant ? 2 : (S.wide ? 1 : 0);
+    const size_t smem_walk = walk_nodes ? 0 : walk_smem_bytes(S);
+    const void *k_walk = walk_kernel_ptr<R, 0>(count_tests);
     if constexpr (sizeof(R) == 4) {
-        if (wide_walk) k_walk = count_tests ? (const void *)extend_walk_kernel<R, true, true> : (const void *)extend_walk_kernel<R, false, true>;
+        if (walk_nodes == 1) k_walk = walk_kernel_ptr<R, 1>(count_tests);
+        if (walk_nodes == 2) k_walk = walk_kernel_ptr<R, 2>(count_tests);
     }
     if ((e = persistent_grid(k_walk, T, smem_walk, &g_walk))) return e;
     if ((e = persistent_grid((const void *)accumulate_kernel<R>, T, 0, &g_simple))) return e;
@@ -326,23 +343,10 @@ cudaError_t render_path_impl(const b2rt_scene *s, const double *cam, const PathA
                 unsigned *cursor = (unsigned *)(fetch + b);
                 bool launched = false;
                 if constexpr (sizeof(R) == 4) {
-                    if (wide_walk) {
-                        if (count_tests)
-                            extend_walk_kernel<R, true, true><<<g_walk, T, 0, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b,
-                                                                                     Q.perm, cursor, Q.tally + 2);
-                        else
-                            extend_walk_kernel<R, false, true><<<g_walk, T, 0, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b,
-                                                                                      Q.perm, cursor, nullptr);
-                        launched = true;
-                    }
+                    if (walk_nodes == 1) { launch_walk<R, 1>(count_tests, g_walk, T, 0, st, S, Q, buf, b, cursor); launched = true; }
+                    if (walk_nodes == 2) { launch_walk<R, 2>(count_tests, g_walk, T, 0, st, S, Q, buf, b, cursor); launched = true; }
                 }
-                if (launched) {
-                } else if (count_tests)
-                    extend_walk_kernel<R, true, false><<<g_walk, T, smem_walk, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
-                                                                                      cursor, Q.tally + 2);
-                else
-                    extend_walk_kernel<R, false, false><<<g_walk, T, smem_walk, st>>>(S, Q.ro[buf], Q.rd[buf], Q.hit, Q.counts + b, Q.perm,
-                                                                                       cursor, nullptr);
+                if (!launched) launch_walk<R, 0>(count_tests, g_walk, T, smem_walk, st, S, Q, buf, b, cursor);
                 prof_end(st);
                 prof_begin(kShade, st);
                 shade_kernel<R, Rng, 0><<<g_shade, T, 0, st>>>(S, Q, buf, b, a.max_depth, PA);

@@ -318,21 +318,27 @@ inline __host__ __device__ int walk_top_staged(int n_top) {
 inline size_t walk_smem_bytes(const SceneDev &S) {
     return (size_t)walk_top_staged(S.n_top) * 64 + (size_t)kWalkSmemStack * 256 * sizeof(int);
 }
-template <typename R, bool COUNT, bool WIDE>
-__global__ void __launch_bounds__(256, sizeof(R) == 4 ? (WIDE ? B2RT_WIDE_MIN_BLOCKS : B2RT_WALK_MIN_BLOCKS) : 1)
+// NODES selects the node format of the box step: 0 = binary 64 B nodes (S.nodes / S.top), 1 = 4-wide 128 B nodes (S.wide),
+// 2 = QUANTISED binary nodes of 32 B (S.quant, lbvh.cu:quantize_kernel): both child boxes as 16-bit cell indices on a grid
+// over the scene bounds, rounded outward by a whole cell, so one node is TWO 16-byte loads (two L1 sector accesses per lane
+// instead of four — the walk is bound by the L1 data pipe, one wavefront per sector access) and a slab plane is one FFMA,
+// t = q * (scale / d) + (base - o) / d.  The boxes only grow, so the closest hit is unchanged.
+template <typename R, bool COUNT, int NODES>
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? (NODES == 1 ? B2RT_WIDE_MIN_BLOCKS : B2RT_WALK_MIN_BLOCKS) : 1)
 extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *__restrict__ rd,
                    real4<R> *__restrict__ hit, const unsigned long long *__restrict__ count,
                    const int *__restrict__ perm, unsigned *__restrict__ next, unsigned long long *tally) {
     unsigned n_node = 0, n_leaf = 0;
     extern __shared__ float4 s_top[];
-    const int n_stage = WIDE ? 0 : walk_top_staged(S.n_top);
-    if (!WIDE) {
+    constexpr bool WIDE = NODES == 1, QUANT = NODES == 2;
+    const int n_stage = (WIDE || QUANT) ? 0 : walk_top_staged(S.n_top);
+    if (!WIDE && !QUANT) {
         for (int i = threadIdx.x; i < 4 * n_stage; i += blockDim.x) s_top[i] = __ldg(S.top + i);
         __syncthreads();
     }
     constexpr int kDone = (int)0x80000000;                       // below every leaf reference (~prim)
     constexpr int kDepth = WIDE ? kWideStackDepth : kStackDepth;
-    constexpr int kShared = WIDE ? 0 : kWalkSmemStack;           // stack entries [0, kShared) live in shared memory
+    constexpr int kShared = (WIDE || QUANT) ? 0 : kWalkSmemStack;    // stack entries [0, kShared) live in shared memory
     const int n = (int)(*count & 0xffffffffULL);
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const R t_min = R(0.001);
@@ -340,7 +346,7 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
     int *s_stack = reinterpret_cast<int *>(s_top + 4 * n_stage) + threadIdx.x;     // entry k at s_stack[k * 256]
     int sp = 0, ref = kDone, pos = -1;
     Ray<R> r; r.o = {R(0), R(0), R(0)}; r.d = r.o;
-    V3<R> id = r.o;
+    V3<R> id = r.o, qa = r.o, qb = r.o;
     Hit<R> best; best.t = R(0); best.a = R(0); best.b = R(0); best.prim = -1;
     bool exhausted = false;                                      // warp-uniform: the queue has no rays left
     auto push = [&](int v) {
@@ -375,6 +381,11 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                     const real4<R> a = ld_stream(ro + j), b = ld_stream(rd + j);
                     r.o = xyz<R>(a); r.d = xyz<R>(b);
                     id = {rcp_(r.d.x), rcp_(r.d.y), rcp_(r.d.z)};
+                    if constexpr (QUANT) {                       // slab plane of cell index q: t = q * qa + qb
+                        const float4 q_base = __ldg(S.quant), q_scale = __ldg(S.quant + 1);     // grid header (uniform, cached)
+                        qa = {R(q_scale.x) * id.x, R(q_scale.y) * id.y, R(q_scale.z) * id.z};
+                        qb = {(R(q_base.x) - r.o.x) * id.x, (R(q_base.y) - r.o.y) * id.y, (R(q_base.z) - r.o.z) * id.z};
+                    }
                     best.t = R(1000000.0); best.prim = -1; best.a = R(0); best.b = R(0);
                     sp = 0; push(kDone);
                     // a dead entry (unused remainder of a producer warp's chunk, slot word -1) is no ray at all
@@ -419,6 +430,34 @@ extend_walk_kernel(SceneDev S, const real4<R> *__restrict__ ro, const real4<R> *
                     if (t2 < kMiss) push(c2);
                     if (t1 < kMiss) push(c1);
                     ref = t0 < kMiss ? c0 : pop();
+                }
+            } else if constexpr (QUANT) {
+                if (ref >= 0) {
+                    if (COUNT) ++n_node;
+                    const uint4 *p = reinterpret_cast<const uint4 *>(S.quant) + 2 + 2 * (size_t)ref;
+                    const uint4 w0 = __ldg(p), w1 = __ldg(p + 1);      // (L.x L.y L.z R.x) (R.y R.z refL refR), lo | hi << 16
+                    // 16-bit cell index -> float without the conversion unit: 0x4B000000 | q is the float 2^23 + q exactly
+                    auto lo = [](unsigned w) { return R(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f); };
+                    auto hi = [](unsigned w) { return R(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f); };
+                    const R lx0 = fma_(lo(w0.x), qa.x, qb.x), lx1 = fma_(hi(w0.x), qa.x, qb.x);
+                    const R ly0 = fma_(lo(w0.y), qa.y, qb.y), ly1 = fma_(hi(w0.y), qa.y, qb.y);
+                    const R lz0 = fma_(lo(w0.z), qa.z, qb.z), lz1 = fma_(hi(w0.z), qa.z, qb.z);
+                    const R rx0 = fma_(lo(w0.w), qa.x, qb.x), rx1 = fma_(hi(w0.w), qa.x, qb.x);
+                    const R ry0 = fma_(lo(w1.x), qa.y, qb.y), ry1 = fma_(hi(w1.x), qa.y, qb.y);
+                    const R rz0 = fma_(lo(w1.y), qa.z, qb.z), rz1 = fma_(hi(w1.y), qa.z, qb.z);
+                    const R tl = max_(max_(min_(lx0, lx1), min_(ly0, ly1)), max_(min_(lz0, lz1), t_min));
+                    const R fl = min_(min_(max_(lx0, lx1), max_(ly0, ly1)), min_(max_(lz0, lz1), best.t));
+                    const R tr = max_(max_(min_(rx0, rx1), min_(ry0, ry1)), max_(min_(rz0, rz1), t_min));
+                    const R fr = min_(min_(max_(rx0, rx1), max_(ry0, ry1)), min_(max_(rz0, rz1), best.t));
+                    const bool hl = tl <= fl, hr = tr <= fr;
+                    const int cl = (int)w1.z, cr = (int)w1.w;
+                    if (hl && hr) {
+                        const bool swap = tr < tl;
+                        push(swap ? cl : cr);
+                        ref = swap ? cr : cl;
+                    } else if (hl) ref = cl;
+                    else if (hr) ref = cr;
+                    else ref = pop();
                 }
             } else {
 #pragma unroll

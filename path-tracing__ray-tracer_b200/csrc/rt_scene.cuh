@@ -52,6 +52,7 @@ struct SceneDev {
     const int4 *tex_info;
     const float4 *nodes, *top;
     const float4 *wide;                // 4-wide nodes (b2rt_lbvh_widen) or nullptr
+    const float4 *quant;               // quantised 32 B nodes behind a 32 B header (b2rt_lbvh_quantize) or nullptr
     int n_top, root;
     int scan_incoherent;
     int n_outside;                     // rectangles [0, n_outside) are not in the hierarchy: tested before every walk
@@ -77,6 +78,7 @@ inline SceneDev make_scene_dev(const b2rt_scene *s) {
     d.nodes = reinterpret_cast<const float4 *>(s->d_bvh_nodes);
     d.top = reinterpret_cast<const float4 *>(s->d_bvh_top);
     d.wide = reinterpret_cast<const float4 *>(s->d_bvh_wide);
+    d.quant = reinterpret_cast<const float4 *>(s->d_bvh_quant);
     d.n_top = s->n_bvh_top; d.root = s->bvh_root;
     d.scan_incoherent = s->scan_incoherent;
     d.n_outside = s->bvh_rects_outside ? s->n_rect : 0;

@@ -445,9 +445,9 @@ def test_scene_struct_carries_size_and_abi_version():
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "t.c")
         open(src, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "b200rt.h"\n'
-                             'int main(void){printf("%zu %zu %zu %zu", sizeof(b2rt_scene), offsetof(b2rt_scene, bounds_hi), sizeof(b2rt_prepare_layout), offsetof(b2rt_scene, d_bvh_wide));return 0;}')
+                             'int main(void){printf("%zu %zu %zu %zu %zu", sizeof(b2rt_scene), offsetof(b2rt_scene, bounds_hi), sizeof(b2rt_prepare_layout), offsetof(b2rt_scene, d_bvh_wide), offsetof(b2rt_scene, d_bvh_quant));return 0;}')
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", os.path.join(d, "t")], check=True)
-        size, off, lay, off_wide = (int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True).stdout.split())
+        size, off, lay, off_wide, off_quant = (int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True).stdout.split())
     assert size == C.sizeof(_lib.SceneStruct) and off == _lib.SceneStruct.bounds_hi.offset
-    assert off_wide == _lib.SceneStruct.d_bvh_wide.offset
+    assert off_wide == _lib.SceneStruct.d_bvh_wide.offset and off_quant == _lib.SceneStruct.d_bvh_quant.offset
     assert lay == C.sizeof(_lib.PrepareLayout)
