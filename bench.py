@@ -358,22 +358,31 @@ def extra_c4(dev, steps: int = 2):
 
 def extra_c4_node_formats(dev, steps: int = 2):
     """The persistent walk kernel of config 4 on its three node formats — binary 64 B (default), quantised 32 B
-    (``quant_walk``), 4-wide 128 B (``wide_walk``): float sums of a 960x540 x 4 spp x depth 4 render compared bit for bit
-    with the default, then the walk kernel's ms per 1080p x 64 spp x depth 4 step (profiles/r2_c4_walk_kernel_analysis.md)."""
+    (``quant_walk``), 4-wide 128 B (``wide_walk``) — and on the default format with the mesh's faces in Morton order: float
+    sums of a 960x540 x 4 spp x depth 4 render compared bit for bit with the default, then the walk kernel's ms per
+    1080p x 64 spp x depth 4 step (profiles/r2_c4_walk_kernel_analysis.md)."""
     import numpy as np
     import torch
     from b200rt import _lib, renderer, scenes
     from b200rt.scene_api import RenderSettings
+    import copy
+    from b200rt.packer import TriangleMesh
     lib = _lib.load()
-    scene, b = scenes.heightfield_scene()
+    scene0, b = scenes.heightfield_scene()
+    # the same mesh with its faces listed along a Morton curve (TriangleMesh.spatially_sorted): neighbours in space are
+    # neighbours in the triangle records; closest hits are the same except for exact ties on shared edges
+    scene1 = copy.copy(scene0)
+    scene1.objects = [o.spatially_sorted() if isinstance(o, TriangleMesh) else o for o in scene0.objects]
     cam = b.create_camera(1920 / 1080)
     out, ref, ws = {}, None, None
-    for name, kw in (("binary_64B", {}), ("quantised_32B", {"quant_walk": True}), ("wide_128B", {"wide_walk": True})):
+    for name, kw, scene in (("binary_64B", {}, scene0), ("quantised_32B", {"quant_walk": True}, scene0),
+                            ("wide_128B", {"wide_walk": True}, scene0), ("binary_64B_morton_face_order", {}, scene1)):
         r = renderer.B200PathTracer(precision="f32", seed=3, device=dev, distributed=False, **kw)
         acc, cnt = r.render_accum(scene, cam, RenderSettings(960, 540, 4, 4))
         if ref is None:
             ref = (acc, cnt)
         same = bool(np.array_equal(acc, ref[0]) and np.array_equal(cnt[:4], ref[1][:4]))
+        differing = int((np.abs(acc[..., :3] - ref[0][..., :3]).max(axis=2) > 0).sum())
         if ws is not None:
             r._ws = ws
         st = r.prepare(scene, cam, RenderSettings(1920, 1080, 64, 4))
@@ -389,8 +398,8 @@ def extra_c4_node_formats(dev, steps: int = 2):
         e1.record(); torch.cuda.synchronize(dev)
         lib.b2rt_profile_read(ms, nl)
         lib.b2rt_profile_enable(0)
-        out[name] = {"sums_identical_to_binary": same, "walk_kernel_ms_per_step": ms[1] / steps,
-                     "ms_per_step": e0.elapsed_time(e1) / steps}
+        out[name] = {"sums_identical_to_binary": same, "pixels_differing": differing, "walk_kernel_ms_per_step": ms[1] / steps,
+                     "bounce0_and_shade_ms_per_step": ms[2] / steps, "ms_per_step": e0.elapsed_time(e1) / steps}
         del r, st
     return out
 

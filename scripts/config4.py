@@ -9,15 +9,18 @@ from b200rt import _lib, packer, renderer, scenes
 from b200rt.device import DeviceScene, current_stream_ptr
 from b200rt.scene_api import RenderSettings
 
-kw = dict(W=1920, H=1080, spp=64, depth=4, steps=2, check=4096, top=512, sort=1, fwalk=0, wprim=0, rout=1, rot=1, wide=1)
+kw = dict(W=1920, H=1080, spp=64, depth=4, steps=2, check=4096, top=512, sort=1, fwalk=0, wprim=0, rout=1, rot=1, wide=0, quant=0, morton=0)
 for a in sys.argv[1:]:
     k, v = a.split("="); kw[k] = type(kw[k])(v)
 lib = _lib.load()
 dev = torch.device("cuda", 0)
 t0 = time.perf_counter(); scene, b = scenes.heightfield_scene(); cam = b.create_camera(kw["W"] / kw["H"])
+if kw["morton"]:                                              # faces of the mesh along a Morton curve (TriangleMesh.spatially_sorted)
+    scene.objects = [o.spatially_sorted() if isinstance(o, packer.TriangleMesh) else o for o in scene.objects]
 t_scene = time.perf_counter() - t0
 t0 = time.perf_counter(); pk = packer.pack_scene(scene, "numba"); t_pack = time.perf_counter() - t0
-ds = DeviceScene(pk, _lib.P_F32, dev, kw["top"], ray_origin_extent=50.0, rects_outside=bool(kw["rout"]), lbvh_rotations=bool(kw["rot"]))
+ds = DeviceScene(pk, _lib.P_F32, dev, kw["top"], ray_origin_extent=50.0, rects_outside=bool(kw["rout"]), lbvh_rotations=bool(kw["rot"]),
+                 wide_nodes=bool(kw["wide"]), quant_nodes=bool(kw["quant"]))
 # ---- LBVH build timing (CUDA events around the whole build call, 5 repetitions)
 n = pk.n_prims
 need = C.c_size_t(0); lib.b2rt_lbvh_temp_bytes(n, C.byref(need))
@@ -45,7 +48,7 @@ a_ids, a_rec = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=1, packe
 b_ids, b_rec = renderer.trace_rays(scene, o, d, "numba", "f32", use_bvh=0, packed=pk)
 same = bool(np.array_equal(a_ids, b_ids) and np.array_equal(a_rec[:, 0], b_rec[:, 0]))
 # ---- path tracing throughput
-r = renderer.B200PathTracer(precision="f32", top_nodes=kw["top"], sort_rays=bool(kw["sort"]), fused_walk=bool(kw["fwalk"]), walk_primary=bool(kw["wprim"]), rects_outside=bool(kw["rout"]), lbvh_rotations=bool(kw["rot"]), wide_walk=bool(kw["wide"]))
+r = renderer.B200PathTracer(precision="f32", top_nodes=kw["top"], sort_rays=bool(kw["sort"]), fused_walk=bool(kw["fwalk"]), walk_primary=bool(kw["wprim"]), rects_outside=bool(kw["rout"]), lbvh_rotations=bool(kw["rot"]), wide_walk=bool(kw["wide"]), quant_walk=bool(kw["quant"]))
 st = r.prepare(scene, cam, RenderSettings(kw["W"], kw["H"], kw["spp"], kw["depth"]))
 r.accumulate(st); torch.cuda.synchronize()
 st["counters"].zero_(); lib.b2rt_profile_enable(1)
@@ -66,5 +69,5 @@ print(json.dumps({
     "mpaths_per_s": cnt[0] / dt / 1e6, "mrays_per_s": (cnt[1] + cnt[2]) / dt / 1e6, "rays_per_path": float((cnt[1] + cnt[2]) / cnt[0]),
     "ms_per_step": dt / kw["steps"] * 1e3, "wave": st["wave"],
     "kernel_ms_per_step": {k: ms[i] / kw["steps"] for i, k in enumerate(["raygen", "extend", "bounce", "shadow", "accumulate", "sort"])},
-    "sort_rays": kw["sort"], "fused_walk": kw["fwalk"], "walk_primary": kw["wprim"], "rects_outside": kw["rout"], "lbvh_rotations": kw["rot"], "wide_walk": kw["wide"],
+    "sort_rays": kw["sort"], "fused_walk": kw["fwalk"], "walk_primary": kw["wprim"], "rects_outside": kw["rout"], "lbvh_rotations": kw["rot"], "wide_walk": kw["wide"], "quant_walk": kw["quant"], "morton_face_order": kw["morton"],
 }))

@@ -451,3 +451,45 @@ def test_scene_struct_carries_size_and_abi_version():
     assert size == C.sizeof(_lib.SceneStruct) and off == _lib.SceneStruct.bounds_hi.offset
     assert off_wide == _lib.SceneStruct.d_bvh_wide.offset and off_quant == _lib.SceneStruct.d_bvh_quant.offset
     assert lay == C.sizeof(_lib.PrepareLayout)
+
+
+def test_morton_face_order_is_a_locality_improving_permutation_with_the_same_hits():
+    """TriangleMesh.spatially_sorted(): a permutation of the faces (adaptive-bit Morton curve) that keeps every closest
+    hit — same distance, the same face through the permutation — and makes consecutive faces spatial neighbours."""
+    from b200rt import packer, scenes
+    from b200rt.scene_api import Scene
+    from oracle import cpu_oracle as O
+    mesh = scenes.heightfield_mesh(41, 21, seed=5)                   # 1 600 triangles, listed as two half-meshes
+    order = packer.morton_face_order(mesh.vertices, mesh.faces)
+    assert sorted(order.tolist()) == list(range(mesh.faces.shape[0]))
+    sorted_mesh = mesh.spatially_sorted()
+    assert np.array_equal(sorted_mesh.faces, mesh.faces[order]) and np.array_equal(sorted_mesh.vertices, mesh.vertices)
+
+    def block_extent(m, k=16):                                       # mean xz bounding-box diagonal of k consecutive faces
+        c = m.vertices[m.faces].mean(1)[:, [0, 2]]
+        c = c[: len(c) // k * k].reshape(-1, k, 2)
+        return float(np.linalg.norm(c.max(1) - c.min(1), axis=1).mean())
+    assert block_extent(sorted_mesh) < 0.5 * block_extent(mesh)
+    # closest hits through the oracle's brute-force scan, float64
+    rng = np.random.default_rng(1)
+    n = 2000
+    o = np.stack([rng.uniform(-14, 14, n), np.full(n, 5.0), rng.uniform(-14, 14, n)], 1)
+    d = np.stack([rng.normal(0, 0.3, n), -np.ones(n), rng.normal(0, 0.3, n)], 1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    hits = []
+    from b200rt.cornell import CustomSceneBuilder
+    cam = CustomSceneBuilder(texture_dir=False).create_camera(1.0)
+    for m in (mesh, sorted_mesh):
+        sc = Scene()
+        sc.objects.append(m)
+        ids, rec = O.nb_scene_hit_rays(O.nb_pack(sc, cam), o, d)
+        hits.append((ids, rec[:, 0]))
+    (ia, ta), (ib, tb) = hits
+    assert np.array_equal(ta, tb) and (ia >= 0).mean() > 0.5
+    hit = ia >= 0
+    assert np.array_equal(hit, ib >= 0)
+    same_face = order[ib[hit]] == ia[hit]
+    assert same_face.mean() > 0.999                                  # anything else is an exact tie on a shared edge
+    # degenerate input: all centroids equal -> identity; empty mesh -> empty permutation
+    assert np.array_equal(packer.morton_face_order(np.zeros((3, 3)), np.array([[0, 1, 2], [0, 1, 2]])), [0, 1])
+    assert packer.morton_face_order(np.zeros((0, 3)), np.zeros((0, 3), np.int64)).shape == (0,)
