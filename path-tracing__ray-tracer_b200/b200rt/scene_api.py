@@ -417,19 +417,24 @@ class Scene:
     def add_object(self, obj: Hittable):
         self.objects.append(obj)
 
-    def add_mesh(self, vertices, faces, material, uvs=None):
+    def add_mesh(self, vertices, faces, material, uvs=None, spatial_order: bool = False):
         """Bulk triangle ingestion: one ``packer.TriangleMesh`` entry in ``objects`` that the packer
         expands, vectorised, into ``len(faces)`` triangles — the object-per-triangle API (``add_object(Triangle(..))``,
-        ``core/scene.py:35-36``) cannot express million-triangle scenes in reasonable time.  Returns the mesh."""
+        ``core/scene.py:35-36``) cannot express million-triangle scenes in reasonable time.  ``spatial_order`` lists the
+        faces along a Morton curve first (``TriangleMesh.spatially_sorted``).  Returns the mesh."""
         from .packer import TriangleMesh
         mesh = TriangleMesh(vertices, faces, material, uvs)
+        if spatial_order:
+            mesh = mesh.spatially_sorted()
         self.objects.append(mesh)
         return mesh
 
-    def add_obj(self, path: str, material, scale: float = 1.0, translate=(0.0, 0.0, 0.0)):
+    def add_obj(self, path: str, material, scale: float = 1.0, translate=(0.0, 0.0, 0.0), spatial_order: bool = False):
         """``add_mesh`` from a Wavefront OBJ file (``packer.load_obj``)."""
         from .packer import load_obj
         mesh = load_obj(path, material, scale, translate)
+        if spatial_order:
+            mesh = mesh.spatially_sorted()
         self.objects.append(mesh)
         return mesh
 

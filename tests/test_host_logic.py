@@ -490,6 +490,8 @@ def test_morton_face_order_is_a_locality_improving_permutation_with_the_same_hit
     assert np.array_equal(hit, ib >= 0)
     same_face = order[ib[hit]] == ia[hit]
     assert same_face.mean() > 0.999                                  # anything else is an exact tie on a shared edge
+    sc = Scene()
+    assert np.array_equal(sc.add_mesh(mesh.vertices, mesh.faces, mesh.material, spatial_order=True).faces, sorted_mesh.faces)
     # degenerate input: all centroids equal -> identity; empty mesh -> empty permutation
     assert np.array_equal(packer.morton_face_order(np.zeros((3, 3)), np.array([[0, 1, 2], [0, 1, 2]])), [0, 1])
     assert packer.morton_face_order(np.zeros((0, 3)), np.zeros((0, 3), np.int64)).shape == (0,)
